@@ -1,0 +1,215 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference here.
+
+Runs only where /root/reference exists (this container).  For each case it
+feeds seeded synthetic predictions (patchperpix_b200/synth.py) to the
+reference's `to_instance_seg` (vote_instances.py:150) with `cuda=True`, the
+kernels compiled for the host through oracle/ref_shim (SURVEY.md §8c Route 2b),
+and records every intermediate of the path: un-normalised consensus sums, vote
+counters, normalised consensus, rank scores, ranked order, selected patches
+after cover / after thinning, patch pairs, patch affinities, instance labels.
+The vectors are stored compactly (gated fg rows x positive offsets, see
+patchperpix_b200/layout.py); big cases keep a seeded sample of rows.
+
+usage: python tools/gen_golden.py [case ...]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_runner            # noqa: E402
+from patchperpix_b200 import synth, layout  # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+# name -> (synth kwargs, patchshape, reference kwargs overrides, max_rows)
+CASES = {
+    # the survey's two-disc probe, flylight flags
+    'discs2d_ps9': (dict(kind='discs', seed=1), (1, 9, 9), {}, None),
+    # crossing worms with overlap voxels, heavy noise, flylight flags
+    'worms2d_ps9_hard': (dict(kind='worms', seed=5, shape=(72, 96), n_worms=5,
+                              width=(5, 8), length=(40, 80), hard_frac=0.15),
+                         (1, 9, 9), {}, None),
+    # the C2 patch size (1x41x41) on a small image
+    'worms2d_ps41': (dict(kind='worms', seed=7, shape=(96, 128), n_worms=4,
+                          width=(8, 11), length=(60, 110)),
+                     (1, 41, 41), {}, 64),
+    # flylight-shaped 3-D block, 7^3 patches
+    'neurites3d_ps7': (dict(kind='neurites', seed=11, shape=(20, 36, 36), n=4,
+                            radius=(1.5, 2.5), seg_len=10.0, n_seg=6),
+                       (7, 7, 7), {}, None),
+    # anisotropic 3-D patches, th 0.7 with the 1-th background band, plain
+    # probability product, interleaved counter, integer rank counter
+    'blobs3d_ps355_inv': (dict(kind='blobs', seed=13, shape=(10, 28, 28), n=6,
+                               rad_xy=(4, 7), rad_z=(1.5, 3), hard_frac=0.2),
+                          (3, 5, 5),
+                          dict(patch_threshold=0.7, fc_threshold=0.6,
+                               vi_bg_use_inv_th=True,
+                               vi_bg_use_less_than_th=False,
+                               consensus_norm_prob_product=False,
+                               consensus_prob_product=True,
+                               consensus_interleaved_cnt=True,
+                               rank_int_counter=True), None),
+    # plain vote counter (no probability product), th/2 background, no
+    # normalisation anywhere, no overlap handling, dense cover thresholds
+    'worms2d_ps7_counter': (dict(kind='worms', seed=17, shape=(64, 64),
+                                 n_worms=4, width=(5, 8), length=(30, 60),
+                                 hard_frac=0.1),
+                            (1, 7, 7),
+                            dict(vi_bg_use_inv_th=False, vi_bg_use_half_th=True,
+                                 vi_bg_use_less_than_th=False,
+                                 consensus_norm_prob_product=False,
+                                 consensus_prob_product=False,
+                                 consensus_norm_aff=False,
+                                 consensus_interleaved_cnt=False,
+                                 rank_norm_patch_score=False,
+                                 patch_graph_norm_aff=False,
+                                 overlapping_inst=False,
+                                 select_patches_for_sparse_data=False), None),
+}
+
+
+def run_case(name, S, rec):
+    skw, ps, over, max_rows = CASES[name]
+    ps = np.array(ps)
+    pred, numinst, labels = synth.make_case(patchshape=ps, **skw)
+    kw = S.default_kwargs(**over)
+    th = kw['patch_threshold']
+    mid = int(np.prod(ps)) // 2
+    fg = pred[mid] > th
+    rec.clear()
+    stages = {}
+
+    vi = S.vi
+    orig_cover = S.mods['foreground_cover'].computeForegroundCover
+    orig_thin = S.mods['foreground_cover'].thinOutForegroundCover
+    orig_rank = S.mods['ranked_patches'].rank_patches_by_score
+
+    def cover(*a, **k):
+        res = orig_cover(*a, **k)
+        stages['cover'] = np.array([p[0] for p in res[0]], np.int32).reshape(-1, 3)
+        return res
+
+    def thin(*a, **k):
+        res = orig_thin(*a, **k)
+        stages['thin'] = np.array([p[0] for p in res[0]], np.int32).reshape(-1, 3)
+        return res
+
+    def rank(*a, **k):
+        res = orig_rank(*a, **k)
+        stages['ranked'] = np.array([p[0] for p in res], np.int32).reshape(-1, 3)
+        return res
+
+    vi.computeForegroundCover = cover
+    vi.thinOutForegroundCover = thin
+    S.mods['ranked_patches'].rank_patches_by_score = rank
+    t0 = time.time()
+    try:
+        inst, fgo = vi.to_instance_seg(
+            pred.copy(), fg.copy(), fg.copy(), numinst.copy(), ps.copy(), **kw)
+    finally:
+        vi.computeForegroundCover = orig_cover
+        vi.thinOutForegroundCover = orig_thin
+        S.mods['ranked_patches'].rank_patches_by_score = orig_rank
+    dt = time.time() - t0
+
+    gate = fg.copy()
+    if kw['overlapping_inst']:
+        gate &= ~(numinst > 1)
+    import hashlib
+    p16 = pred.astype(np.float16)
+    out = dict(
+        pred_sha1=hashlib.sha1(p16.tobytes()).hexdigest(), numinst=numinst,
+        patchshape=ps.astype(np.int32),
+        kwargs=json.dumps({k: v for k, v in kw.items()
+                           if isinstance(v, (bool, int, float, str))}),
+        synth=json.dumps({k: (list(v) if isinstance(v, tuple) else v)
+                          for k, v in skw.items()}),
+        instances=inst, gate=gate,
+    )
+    if p16.nbytes <= (1 << 20):     # big inputs are regenerated from `synth`
+        out['pred_f16'] = p16
+    rows = np.arange(int(gate.sum()))
+    if max_rows is not None and len(rows) > max_rows:
+        rows = np.sort(np.random.default_rng(0).choice(
+            len(rows), max_rows, replace=False))
+    out['rows'] = rows.astype(np.int32)
+    sn = rec.result()
+    if sn.get('cons_raw') is not None:
+        out['cons_raw'] = layout.dense_to_compact(sn['cons_raw'], gate, ps)[rows]
+    if sn.get('cnt') is not None:
+        c = layout.dense_to_compact(sn['cnt'], gate, ps)[rows]
+        assert np.all(c == np.round(c)) and c.max() < 65536
+        out['cnt'] = c.astype(np.uint16)
+    if sn.get('cons_norm') is not None:
+        out['cons_norm'] = layout.dense_to_compact(sn['cons_norm'], gate, ps)[rows]
+    # whole-array checksums (double) so that sampled cases still pin the total
+    for key in ('cons_raw', 'cnt', 'cons_norm'):
+        if sn.get(key) is not None:
+            out[key + '_sum'] = np.float64(sn[key].astype(np.float64).sum())
+            # nothing may be written outside gated rows / positive offsets
+            full = layout.dense_to_compact(sn[key], gate, ps)
+            assert np.isclose(full.astype(np.float64).sum(), out[key + '_sum'],
+                              rtol=1e-9, atol=1e-6), key
+    out['score'] = sn['score']
+    out['pairs'] = sn['pairs']
+    out['aff'] = np.array(sn['aff'])
+    for k in ('ranked', 'cover', 'thin'):
+        if k in stages:
+            out[k] = stages[k]
+    os.makedirs(GOLD, exist_ok=True)
+    fn = os.path.join(GOLD, name + '.npz')
+    np.savez_compressed(fn, **out)
+    print('%-24s %6.1fs  fg=%d gated=%d rows=%d pairs=%d inst=%d  %.2f MB' % (
+        name, dt, int(fg.sum()), int(gate.sum()), len(rows),
+        len(sn['pairs']), len(np.unique(inst)) - 1,
+        os.path.getsize(fn) / 1e6))
+
+
+class Recorder:
+    """snapshots kernel outputs in launch order (see ref_runner._Kernel)."""
+
+    def __init__(self):
+        self.clear()
+
+    def clear(self):
+        self.d = {}
+
+    def result(self):
+        return self.d
+
+    def __call__(self, kind, options, args):
+        arrs = [a for a in args]
+        if kind == 'K_FILL':
+            if '-DOUTPUT_BOTH' in options:
+                self.d['cons_raw'] = np.array(arrs[-2])
+                self.d['cnt'] = np.array(arrs[-1])
+            elif '-DOUTPUT_CNT' in options:
+                self.d['cnt'] = np.array(arrs[-1])
+            else:
+                self.d['cons_raw'] = np.array(arrs[-1])
+        elif kind == 'K_NORM':
+            self.d['cons_norm'] = np.array(arrs[1])
+        elif kind == 'K_RANK':
+            self.d['score'] = np.array(arrs[-1])
+        elif kind == 'K_GRAPH':
+            self.d['aff'] = np.asarray(arrs[2])     # filled slice by slice
+            self.d['pairs'] = np.array(arrs[3])
+
+
+def main():
+    names = sys.argv[1:] or list(CASES)
+    rec = Recorder()
+    S = ref_runner.RefSession(recorder=rec)
+    for n in names:
+        run_case(n, S, rec)
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())
