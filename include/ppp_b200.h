@@ -1,0 +1,162 @@
+/* ppp_b200.h — C ABI of the B200-native PatchPerPix instance-assembly path.
+ *
+ * This is the device boundary that replaces the reference's pycuda layer
+ * (PatchPerPix/vote_instances/cuda_code.py:5-59) and the three operator
+ * functions that sit on it:
+ *   create_consensus_array_cuda   consensus_array.py:71-206
+ *   rank_patches_cuda             ranked_patches.py:33-74
+ *   computePatchGraph_cuda        aff_patch_graph.py:113-187
+ * plus device versions of the serial host steps that separate them
+ * (foreground_cover.py:15-256, graph_to_labeling.py:34-155).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *    the name ends in _h; the caller owns every buffer, nothing is allocated
+ *    or freed behind its back (the reference leaks managed memory instead,
+ *    SURVEY.md §8b "Ownership");
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it;
+ *  - return value 0 = success, otherwise a cudaError_t (or -1 for argument
+ *    errors); ppp_last_error() gives the text;
+ *  - volumes are [Z][Y][X] row-major, predictions [P][Z][Y][X] float32 with
+ *    P = psz*psy*psx exactly as the reference feeds them
+ *    (vote_instances.py:193-200).
+ *
+ * Data layout produced by this library
+ *  - "row" = one foreground voxel (pred[mid] > TH, or a host-side candidate),
+ *    rows in raster order;
+ *    fgidx[v] = row or -1; rowvox[row] = v.
+ *  - flags[v]: bit0 fg, bit1 gated (fg and not overlap,
+ *    fillConsensusArray.cu:53-60), bit2 valid patch centre (fg and interior,
+ *    fillConsensusArray.cu:25-33).
+ *  - dp[row][P]: the patch of that centre, class-folded: v if "high"
+ *    (v > TH), -(1-v) if "background" (the USE_*_TH test), 0 otherwise or if
+ *    the pixel it talks about is not gated.
+ *  - cons[row][K], cnt[row][K]: consensus of base voxel `row` with the voxel
+ *    at the k-th lexicographically positive offset; cnt packs
+ *    (negative votes << 16) | positive votes.
+ */
+#ifndef PPP_B200_H
+#define PPP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPP_FLAG_FG      1
+#define PPP_FLAG_GATED   2
+#define PPP_FLAG_CENTRE  4
+#define PPP_FLAG_CAND    8    /* host-side foreground (candidate patch centre) */
+#define PPP_FLAG_INTERIOR 16  /* at least patchshape//2 away from every face */
+#define PPP_FLAG_ROW     (PPP_FLAG_FG | PPP_FLAG_CAND)
+
+/* kernel variant switches: the reference compiles one kernel per combination
+ * of -D flags (utilVoteInstances.py:389-449); here they are run-time fields. */
+typedef struct ppp_cfg {
+    int32_t Z, Y, X;            /* block shape */
+    int32_t psz, psy, psx;      /* patchshape */
+    float th_gt;                /* "v > TH"  <=> v > th_gt (TH is a double literal) */
+    float bg_lt;                /* background test <=> v < bg_lt (THI, TH/2 or TH) */
+    float fc_gt;                /* host-side patch > fc_threshold (f32-rounded)   */
+    float pt_gt;                /* host-side patch > patch_threshold (f32-rounded) */
+    double th2;                 /* TH*TH         (fillConsensusArray.cu:105) */
+    double one_m_th2;           /* 1.0 - TH*TH */
+    int32_t prod_mode;          /* 0 vote counter, 1 PROB_PRODUCT, 2 NORM_PROB_PRODUCT */
+    int32_t norm_aff;           /* consensus_norm_aff: divide sums by vote count */
+    int32_t use_overlap;        /* -DOVERLAP */
+    int32_t rank_flags;         /* bit0 NORM_PATCH_RANK, bit1 COUNT_POS_NEG */
+    int32_t graph_flags;        /* bit0 NORM_PATCH_AFFINITY */
+    int32_t reserved;
+} ppp_cfg;
+
+const char* ppp_last_error(void);
+int ppp_version(void);
+
+/* ---- step 0: gate + compaction (vote_instances.py:276-287 does this on the
+ * host with np.where + a python list comprehension) ------------------------ */
+/* flags[V] from pred[mid], the optional overlap volume (u8, may be NULL) and
+ * the optional host-side foreground `cand` (u8, may be NULL): voxels the
+ * reference's python side treats as patch candidates even if pred[mid] <= TH
+ * (loadFg / returnFg, utilVoteInstances.py:275-322). */
+int ppp_gate(const float* pred, const uint8_t* overlap, const uint8_t* cand,
+             const ppp_cfg* cfg, uint8_t* flags, void* stream);
+/* exclusive scan of (flags & ROW): fgidx[V], rowvox[<=V], *n_rows (device int64).
+ * scratch: at least ppp_compact_scratch_bytes(V) bytes. */
+int64_t ppp_compact_scratch_bytes(int64_t V);
+int ppp_compact(const uint8_t* flags, int64_t V, int32_t* fgidx, int32_t* rowvox,
+                int64_t* n_rows, void* scratch, void* stream);
+
+/* ---- step 0b: centre-major class-folded patches + bit masks --------------
+ * dp f32 [F][P]; fcmask/ptmask u32 [F][W], W = (P+31)/32: bit po set iff
+ * pred[po][c] > fc_gt / > pt_gt (foreground_cover.py:158, graph_to_labeling.py:84).
+ * Any output pointer may be NULL. */
+int ppp_prepare_patches(const float* pred, const uint8_t* flags,
+                        const int32_t* rowvox, int64_t F, const ppp_cfg* cfg,
+                        float* dp, uint32_t* fcmask, uint32_t* ptmask,
+                        void* stream);
+
+/* ---- step 1: consensus (fillConsensusArray.cu + normConsensusArray.cu) ----
+ * cons f32 [F][K] (normalised iff cfg->norm_aff), cnt u32 [F][K] or NULL. */
+int ppp_consensus(const float* dp, const uint8_t* flags, const int32_t* fgidx,
+                  const int32_t* rowvox, int64_t F, const ppp_cfg* cfg,
+                  float* cons, uint32_t* cnt, void* stream);
+
+/* ---- step 2: rank (rankPatches.cu) ----------------------------------------
+ * score f32 [Z][Y][X]: border voxels -1 / -9999999, non-fg interior 0. */
+int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fgidx,
+             const int32_t* rowvox, int64_t F, const float* cons,
+             const ppp_cfg* cfg, float* score, void* stream);
+/* stable descending sort of the candidate voxels by score
+ * (ranked_patches.py:21-30): cand[n] voxel indices in raster order ->
+ * order[n] = candidate voxel indices, best first.  scratch from
+ * ppp_rank_sort_scratch_bytes(n). */
+int64_t ppp_rank_sort_scratch_bytes(int64_t n);
+int ppp_rank_sort(const float* score, const int32_t* cand, int64_t n,
+                  int32_t* order, void* scratch, void* stream);
+
+/* ---- steps 3+4: greedy foreground cover and thinning ----------------------
+ * mask u8 [V] (mask_to_cover, overlap already removed), overlap u8 [V] or NULL
+ * (centres to skip, foreground_cover.py:144).  order[n] from ppp_rank_sort.
+ * selected u8 [n] in/out (zero it before the first call).
+ * pix_ths[n_pix]: the pixTh schedule (foreground_cover.py:35-39).
+ * scratch: ppp_cover_scratch_bytes(cfg) bytes. */
+int64_t ppp_cover_scratch_bytes(const ppp_cfg* cfg);
+int ppp_cover(const uint8_t* mask, const uint8_t* overlap, const int32_t* order,
+              int64_t n, const int32_t* fgidx, const uint32_t* fcmask,
+              const ppp_cfg* cfg, const int32_t* pix_ths, int32_t n_pix,
+              uint8_t* selected, void* scratch, void* stream);
+/* greedy set cover over the selected patches (foreground_cover.py:183-256):
+ * sel[m] voxel indices in ranked order; keep u8 [m] out.
+ * scratch: ppp_thin_scratch_bytes(cfg, m). */
+int64_t ppp_thin_scratch_bytes(const ppp_cfg* cfg, int64_t m);
+int ppp_thin(const uint8_t* mask, const int32_t* sel, int64_t m,
+             const int32_t* fgidx, const uint32_t* fcmask, const ppp_cfg* cfg,
+             uint8_t* keep, void* scratch, void* stream);
+
+/* ---- step 5: patch graph (computePatchGraph.cu) ---------------------------
+ * pairs u32 [n][6] = (z,y,x,z2,y2,x2); aff f32 [n]. */
+int ppp_patch_graph(const float* pred, const uint8_t* flags,
+                    const int32_t* fgidx, const float* cons,
+                    const uint32_t* pairs, int64_t n, const ppp_cfg* cfg,
+                    float* aff, void* stream);
+
+/* ---- step 6: connected components over aff > 0 and painting ---------------
+ * (aff_patch_graph.py:31-40, graph_to_labeling.py:50-84).  Node = voxel index
+ * of a patch centre.  comp i32 [V] scratch/out: component number (1-based, in
+ * the reference's order) of every node that has a positive edge, else 0.
+ * n_comp device int32.  scratch: ppp_label_scratch_bytes(V, n). */
+int64_t ppp_label_scratch_bytes(int64_t V, int64_t n);
+int ppp_label_cc(const uint32_t* pairs, const float* aff, int64_t n,
+                 const ppp_cfg* cfg, int32_t* comp, int32_t* n_comp,
+                 void* scratch, void* stream);
+/* instances i32 [V] (zeroed by the caller): for every node with comp > 0,
+ * window pixels with pred > pt_gt take max(comp) ("later components overwrite
+ * earlier ones", graph_to_labeling.py:84).  nodes[m] voxel indices. */
+int ppp_paint(const float* pred, const int32_t* nodes, int64_t m,
+              const int32_t* comp, const ppp_cfg* cfg, int32_t* instances,
+              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

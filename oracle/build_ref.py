@@ -1,0 +1,30 @@
+"""TEST INFRASTRUCTURE ONLY — prebuilds the reference kernels for the host
+(oracle/_ref/refk_*.so) from the sources where they lie under /root/reference,
+for the shapes bench.py's `--impl reference` / cpu_baseline legs use.
+oracle/_ref/ is git-ignored but travels to the GPU box with gpurun."""
+from . import ref_runner
+
+# (kind, dims, patchshape, th, flags, omp)
+BASE = ['-DUSE_LESS_THAN_TH', '-DOVERLAP']
+CONFIGS = []
+for dims, ps in (((1, 160, 160), (1, 41, 41)), ((24, 48, 48), (7, 7, 7))):
+    for omp in (False, True):
+        CONFIGS += [
+            ('fill', dims, ps, 0.5, BASE + ['-DNORM_PROB_PRODUCT'], omp),
+            ('fill', dims, ps, 0.5, BASE + ['-DNORM_PROB_PRODUCT', '-DOUTPUT_CNT'], omp),
+            ('norm', dims, ps, 0.5, [], omp),
+            ('rank', dims, ps, 0.5, BASE + ['-DNORM_PATCH_RANK'], omp),
+            ('graph', dims, ps, 0.5, ['-DNORM_PATCH_AFFINITY'], omp),
+        ]
+
+
+def build_all():
+    if not ref_runner.reference_available():
+        print('reference sources absent: keeping prebuilt oracle/_ref')
+        return []
+    return [ref_runner.build_ref_kernel(*c) for c in CONFIGS]
+
+
+if __name__ == '__main__':
+    for p in build_all():
+        print(p)

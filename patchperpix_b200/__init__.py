@@ -1,0 +1,9 @@
+"""patchperpix_b200 — B200-native instance assembly for PatchPerPix.
+
+Drop-in for the reference's `PatchPerPix.vote_instances` package on the
+`run_ppp.py --do decode label` path (PatchPerPix/vote_instances/__init__.py:1-3):
+    patchperpix_b200.vote_instances.main(**kwargs)
+    patchperpix_b200.stitch_patch_graph.main(pred_file, **kwargs)
+"""
+__all__ = ['vote_instances', 'stitch_patch_graph', 'cuda_code', 'assembly',
+           'consensus_array', 'ranked_patches', 'aff_patch_graph', 'synth', 'layout']

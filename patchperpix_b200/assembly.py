@@ -1,0 +1,230 @@
+"""Device pipeline for ONE block: consensus -> rank -> cover -> thin ->
+patch graph -> connected components -> paint, all through the C ABI
+(include/ppp_b200.h).  This is the hot path that `to_instance_seg`
+(vote_instances.py:150-452 in the reference) drives; every stage keeps its
+data on the GPU, only the patch-pair enumeration (scipy cKDTree, exactly as
+aff_patch_graph.py:43-110) touches the host.
+"""
+import ctypes
+
+import numpy as np
+import scipy.spatial
+
+from . import cuda_code as cc
+from .layout import patch_geometry
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class BlockAssembler:
+    """state of one block on the device.
+
+    pred        f32 [P,Z,Y,X] cuda tensor (the block incl. its halo)
+    foreground  host-side foreground (bool/u8 [Z,Y,X] cuda tensor): the
+                candidate patch centres (vote_instances.py:276-287)
+    overlap     u8 [Z,Y,X] cuda tensor, numinst > 1 (vote_instances.py:211)
+    """
+
+    def __init__(self, pred, foreground, overlap, patchshape, **kwargs):
+        torch = _torch()
+        assert pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous()
+        self.pred = pred
+        self.shape = tuple(int(s) for s in pred.shape[1:])
+        self.ps, self.P, self.rad, _, self.N, self.K = patch_geometry(patchshape)
+        assert pred.shape[0] == self.P, "channel count != prod(patchshape)"
+        self.kwargs = kwargs
+        self.cfg = cc.make_cfg(self.shape, self.ps, **kwargs)
+        self.V = int(np.prod(self.shape))
+        self.dev = pred.device
+        self.foreground = foreground.to(torch.uint8).contiguous()
+        self.overlap = overlap.to(torch.uint8).contiguous()
+        self.stream = cc.current_stream_ptr()
+        self.W = (self.P + 31) // 32
+        self.cons = None
+        self.cnt = None
+        self.score = None
+        self._prepared = False
+
+    # -- step 0 ------------------------------------------------------------
+    def prepare(self, want_dp=True):
+        torch = _torch()
+        V = self.V
+        self.flags = torch.empty(V, dtype=torch.uint8, device=self.dev)
+        cc.call('ppp_gate', cc.ptr(self.pred), cc.ptr(self.overlap),
+                cc.ptr(self.foreground), self.cfg, cc.ptr(self.flags), self.stream)
+        self.fgidx = torch.empty(V, dtype=torch.int32, device=self.dev)
+        self.rowvox = torch.empty(V, dtype=torch.int32, device=self.dev)
+        nrows = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        scratch = torch.empty(cc.call('ppp_compact_scratch_bytes', V), dtype=torch.uint8,
+                              device=self.dev)
+        cc.call('ppp_compact', cc.ptr(self.flags), V, cc.ptr(self.fgidx),
+                cc.ptr(self.rowvox), cc.ptr(nrows), cc.ptr(scratch), self.stream)
+        self.F = int(nrows.item())          # the one host sync: sizes the outputs
+        self.rowvox = self.rowvox[:self.F]
+        F = max(self.F, 1)
+        self.dp = torch.empty((F, self.P), dtype=torch.float32, device=self.dev) \
+            if want_dp else None
+        self.fcmask = torch.empty((F, self.W), dtype=torch.int32, device=self.dev)
+        cc.call('ppp_prepare_patches', cc.ptr(self.pred), cc.ptr(self.flags),
+                cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.dp),
+                cc.ptr(self.fcmask), None, self.stream)
+        self._prepared = True
+        return self.F
+
+    # -- step 1 ------------------------------------------------------------
+    def consensus(self, want_cnt=False):
+        """create_consensus_array_cuda (consensus_array.py:71-206)."""
+        torch = _torch()
+        if not self._prepared:
+            self.prepare()
+        F = max(self.F, 1)
+        self.cons = torch.empty((F, self.K), dtype=torch.float32, device=self.dev)
+        self.cnt = torch.empty((F, self.K), dtype=torch.int32, device=self.dev) \
+            if want_cnt else None
+        cc.call('ppp_consensus', cc.ptr(self.dp), cc.ptr(self.flags), cc.ptr(self.fgidx),
+                cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.cons),
+                cc.ptr(self.cnt), self.stream)
+        return self.cons
+
+    # -- step 2 ------------------------------------------------------------
+    def rank(self):
+        """rank_patches_cuda (ranked_patches.py:33-74): score volume."""
+        torch = _torch()
+        self.score = torch.empty(self.shape, dtype=torch.float32, device=self.dev)
+        cc.call('ppp_rank', cc.ptr(self.dp), cc.ptr(self.flags), cc.ptr(self.fgidx),
+                cc.ptr(self.rowvox), self.F, cc.ptr(self.cons), self.cfg,
+                cc.ptr(self.score), self.stream)
+        return self.score
+
+    def candidates(self):
+        """vote_instances.py:276-287: interior foreground voxels, raster order."""
+        torch = _torch()
+        m = (self.flags & 24) == 24      # CAND | INTERIOR
+        return torch.nonzero(m).flatten().to(torch.int32)
+
+    def ranked(self, cand=None, score=None):
+        """rank_patches_by_score (ranked_patches.py:21-30): candidate voxel
+        indices, best score first, ties in raster order."""
+        torch = _torch()
+        cand = self.candidates() if cand is None else cand
+        score = self.score if score is None else score
+        n = int(cand.numel())
+        order = torch.empty(max(n, 1), dtype=torch.int32, device=self.dev)
+        scratch = torch.empty(cc.call('ppp_rank_sort_scratch_bytes', n), dtype=torch.uint8,
+                              device=self.dev)
+        cc.call('ppp_rank_sort', cc.ptr(score), cc.ptr(cand), n, cc.ptr(order),
+                cc.ptr(scratch), self.stream)
+        return order[:n]
+
+    # -- steps 3+4 ---------------------------------------------------------
+    def cover(self, mask, order):
+        """computeForegroundCover (foreground_cover.py:15-180)."""
+        torch = _torch()
+        n = int(order.numel())
+        if n == 0:
+            return order
+        if self.kwargs.get('select_patches_for_sparse_data', False):
+            pix = [0]
+        else:
+            mid = int(self.P / 2)
+            pix = [t for t in [500, 100, 50, 10, 0] if t < mid]
+        pix_t = torch.tensor(pix, dtype=torch.int32, device=self.dev)
+        selected = torch.zeros(n, dtype=torch.uint8, device=self.dev)
+        scratch = torch.empty(cc.call('ppp_cover_scratch_bytes', self.cfg),
+                              dtype=torch.uint8, device=self.dev)
+        mask = mask.to(torch.uint8).contiguous()
+        cc.call('ppp_cover', cc.ptr(mask), cc.ptr(self.overlap), cc.ptr(order), n,
+                cc.ptr(self.fgidx), cc.ptr(self.fcmask), self.cfg, cc.ptr(pix_t),
+                len(pix), cc.ptr(selected), cc.ptr(scratch), self.stream)
+        return order[selected.bool()]
+
+    def thin(self, mask, sel):
+        """thinOutForegroundCover (foreground_cover.py:183-256)."""
+        torch = _torch()
+        m = int(sel.numel())
+        if m == 0:
+            return sel
+        keep = torch.zeros(m, dtype=torch.uint8, device=self.dev)
+        scratch = torch.empty(cc.call('ppp_thin_scratch_bytes', self.cfg, m),
+                              dtype=torch.uint8, device=self.dev)
+        mask = mask.to(torch.uint8).contiguous()
+        sel = sel.contiguous()
+        cc.call('ppp_thin', cc.ptr(mask), cc.ptr(sel), m, cc.ptr(self.fgidx),
+                cc.ptr(self.fcmask), self.cfg, cc.ptr(keep), cc.ptr(scratch), self.stream)
+        return sel[keep.bool()]
+
+    # -- step 4b (host) ------------------------------------------------------
+    def coords(self, vox):
+        """voxel indices (tensor) -> int64 [n,3] numpy (z,y,x)."""
+        v = vox.cpu().numpy().astype(np.int64)
+        Z, Y, X = self.shape
+        return np.stack([v // (Y * X), (v // X) % Y, v % X], axis=1)
+
+    def patch_pairs(self, sel_coords):
+        """computeAndStorePatchPairs (aff_patch_graph.py:43-110).
+
+        `sel_coords` int [m,3] in ranked order.  Returns u32 [n,6] numpy in
+        the reference's order (the python-set iteration order of
+        cKDTree.query_pairs, then the self pairs) or None."""
+        kw = self.kwargs
+        ps = self.ps
+        m = len(sel_coords)
+        if m == 0:
+            return None
+        ordr = np.argsort(sel_coords[:, 2], kind='stable')       # :45
+        pts = sel_coords[ordr].astype(np.uint32)
+        tree = scipy.spatial.cKDTree(pts, leafsize=4)
+        pairs = tree.query_pairs(2 * np.sum(ps), p=1)            # :57
+        max_ps = kw.get("max_total_patch_distance_in_ps_multiples", 2)
+        if len(pairs):
+            pa = np.array(list(pairs), dtype=np.int64).reshape(-1, 2)
+            d = np.abs(pts[pa[:, 0]].astype(np.float32) - pts[pa[:, 1]].astype(np.float32))
+            keep = ~np.any(d > max_ps * ps, axis=1)              # :61-69
+            pa = pa[keep]
+        else:
+            pa = np.zeros((0, 2), np.int64)
+        single = bool(kw.get('includeSinglePatchCCS', False))
+        total = len(pa) + (m if single else 0)
+        if total == 0:
+            return None
+        arr = np.zeros((total, 6), np.uint32)
+        arr[:len(pa), :3] = pts[pa[:, 0]]
+        arr[:len(pa), 3:] = pts[pa[:, 1]]
+        if single:
+            arr[len(pa):, :3] = pts
+            arr[len(pa):, 3:] = pts
+        return arr
+
+    # -- step 5 ------------------------------------------------------------
+    def patch_graph(self, pairs_dev):
+        """computePatchGraph_cuda (aff_patch_graph.py:113-187), matrix form."""
+        torch = _torch()
+        n = int(pairs_dev.shape[0])
+        aff = torch.empty(max(n, 1), dtype=torch.float32, device=self.dev)
+        cc.call('ppp_patch_graph', cc.ptr(self.pred), cc.ptr(self.flags), cc.ptr(self.fgidx),
+                cc.ptr(self.cons), cc.ptr(pairs_dev), n, self.cfg, cc.ptr(aff), self.stream)
+        return aff[:n]
+
+    # -- step 6 ------------------------------------------------------------
+    def label(self, pairs_dev, aff, nodes, pred=None, cfg=None):
+        """setAffgraph + affGraphToInstances (aff_patch_graph.py:31-40,
+        graph_to_labeling.py:50-84).  Returns (instances i32 [Z,Y,X], n_comp)."""
+        torch = _torch()
+        cfg = cfg or self.cfg
+        pred = self.pred if pred is None else pred
+        n = int(pairs_dev.shape[0])
+        V = self.V
+        comp = torch.empty(V, dtype=torch.int32, device=self.dev)
+        ncomp = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        scratch = torch.empty(cc.call('ppp_label_scratch_bytes', V, n), dtype=torch.uint8,
+                              device=self.dev)
+        cc.call('ppp_label_cc', cc.ptr(pairs_dev), cc.ptr(aff), n, cfg, cc.ptr(comp),
+                cc.ptr(ncomp), cc.ptr(scratch), self.stream)
+        inst = torch.zeros(self.shape, dtype=torch.int32, device=self.dev)
+        nodes = nodes.contiguous()
+        cc.call('ppp_paint', cc.ptr(pred), cc.ptr(nodes), int(nodes.numel()), cc.ptr(comp),
+                cfg, cc.ptr(inst), self.stream)
+        return inst, int(ncomp.item())

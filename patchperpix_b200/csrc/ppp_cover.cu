@@ -1,0 +1,335 @@
+// Steps 3+4: greedy foreground cover and greedy set-cover thinning on the
+// device (foreground_cover.py:15-256 are serial python loops over numpy
+// windows).  The decisions are inherently sequential, so both run in ONE CTA;
+// what makes them fast is the data layout: the mask to cover is a bit volume
+// (one 32-bit word per 32 x-voxels, resident in shared memory when it fits)
+// and every candidate patch is a P-bit string (`fcmask`, patch > fc_threshold),
+// so "how many uncovered voxels would this patch cover" is a handful of
+// funnel-shift / AND / POPC per patch row instead of a P-element numpy op.
+#include "ppp_common.cuh"
+#include "ppp_api.cuh"
+
+struct BitVol {
+    uint32_t* w;      // [Z*Y][WX]
+    int WX;           // words per x-row incl. one guard word
+};
+
+__host__ __device__ inline int bitvol_wx(int X) { return (X + 31) / 32 + 1; }
+
+// 32 mask bits starting at bit position `bit` of x-row `r`
+__device__ __forceinline__ uint32_t bv_get32(const BitVol& b, int r, int bit)
+{
+    const uint32_t* p = b.w + (int64_t)r * b.WX + (bit >> 5);
+    return __funnelshift_r(p[0], p[1], bit & 31);
+}
+
+__device__ __forceinline__ void bv_clear32(const BitVol& b, int r, int bit, uint32_t m)
+{
+    uint32_t* p = b.w + (int64_t)r * b.WX + (bit >> 5);
+    int s = bit & 31;
+    p[0] &= ~(m << s);
+    if (s) p[1] &= ~(m >> (32 - s));
+}
+
+// 32 bits of a patch bit string starting at bit `bit` (zero past the end)
+__device__ __forceinline__ uint32_t pm_get32(const uint32_t* __restrict__ pm, int W, int bit)
+{
+    int a = bit >> 5;
+    uint32_t lo = a < W ? pm[a] : 0u;
+    uint32_t hi = (a + 1) < W ? pm[a + 1] : 0u;
+    return __funnelshift_r(lo, hi, bit & 31);
+}
+
+// bits of [x0, x0+nb) that lie inside the radslice x-range [rx, X-rx)
+__device__ __forceinline__ uint32_t rad_xmask(const Geo& g, int x0, int nb)
+{
+    int lo = max(g.rx - x0, 0), hi = min(g.X - g.rx - x0, nb);
+    if (hi <= lo) return 0u;
+    uint32_t m = (hi - lo) >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u);
+    return m << lo;
+}
+
+// One warp: count (and optionally clear) the still-uncovered voxels of the
+// window of centre (cz,cy,cx) that the patch bit string `pm` marks.
+// Returns the warp-wide count; *rad_cleared (lane-local partial, only when
+// clearing) counts cleared voxels inside the radslice.
+template <bool CLEAR>
+__device__ __forceinline__ int patch_window_count(const Geo& g, const BitVol& bv,
+                                                  const uint32_t* __restrict__ pm,
+                                                  int cz, int cy, int cx, int lane,
+                                                  int* rad_cleared)
+{
+    int cnt = 0;
+    const int nrows = g.psz * g.psy;
+    for (int rr = lane; rr < nrows; rr += 32) {
+        int qz = rr / g.psy, qy = rr - qz * g.psy;
+        int z = cz - g.rz + qz, y = cy - g.ry + qy;
+        int r = z * g.Y + y;
+        bool row_in_rad = z >= g.rz && z < g.Z - g.rz && y >= g.ry && y < g.Y - g.ry;
+        for (int j = 0; j < g.psx; j += 32) {
+            int nb = min(32, g.psx - j);
+            uint32_t keep = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+            int x0 = cx - g.rx + j;
+            uint32_t m = bv_get32(bv, r, x0) & pm_get32(pm, g.W, rr * g.psx + j) & keep;
+            cnt += __popc(m);
+            if (CLEAR && m) {
+                bv_clear32(bv, r, x0, m);
+                if (row_in_rad) *rad_cleared += __popc(m & rad_xmask(g, x0, nb));
+            }
+        }
+    }
+    return CLEAR ? cnt : warp_sum_i(cnt);
+}
+
+// pack the u8 mask volume into the bit volume; returns (via *remaining) the
+// number of set voxels inside the radslice
+__device__ void bitvol_init(const Geo& g, const BitVol& bv, const uint8_t* __restrict__ mask,
+                            int* remaining)
+{
+    const int rows = g.Z * g.Y;
+    int local = 0;
+    for (int64_t i = threadIdx.x; i < (int64_t)rows * bv.WX; i += blockDim.x) {
+        int r = (int)(i / bv.WX), wi = (int)(i - (int64_t)r * bv.WX);
+        uint32_t word = 0;
+        int x0 = wi * 32;
+        for (int t = 0; t < 32; t++) {
+            int x = x0 + t;
+            if (x < g.X && mask[(int64_t)r * g.X + x]) word |= 1u << t;
+        }
+        bv.w[i] = word;
+        int z = r / g.Y, y = r - z * g.Y;
+        if (z >= g.rz && z < g.Z - g.rz && y >= g.ry && y < g.Y - g.ry)
+            local += __popc(word & rad_xmask(g, x0, 32));
+    }
+    atomicAdd(remaining, local);
+}
+
+extern "C" int64_t ppp_cover_scratch_bytes(const ppp_cfg* cfg)
+{
+    Geo g = make_geo(*cfg);
+    return (int64_t)g.Z * g.Y * bitvol_wx(g.X) * 4 + 256;
+}
+
+#define COVER_THREADS 1024
+#define THIN_THREADS 256
+#define SMEM_BITVOL_MAX (200 * 1024)
+
+// ---------------------------------------------------------------------------
+// greedy cover (foreground_cover.py:111-180).  A patch is selected iff it
+// covers more than pixTh still-uncovered voxels; the walk over the ranked list
+// stops when nothing inside the radslice is left (:128).
+// The serial walk is kept exact but shortened: coverage counts can only fall
+// while the mask shrinks, so a candidate whose count is already <= pixTh at
+// the start of its chunk is rejected for good.  All 32 warps count a chunk of
+// 1024 candidates in parallel (phase A), then warp 0 replays only the
+// survivors in rank order against the live mask (phase B).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(COVER_THREADS)
+cover_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ overlap,
+             const int32_t* __restrict__ order, int64_t n,
+             const int32_t* __restrict__ fgidx, const uint32_t* __restrict__ fcmask,
+             ppp_cfg cfg, const int32_t* __restrict__ pix_ths, int n_pix,
+             uint8_t* __restrict__ selected, uint32_t* gbits, int use_smem)
+{
+    Geo g = make_geo(cfg);
+    extern __shared__ uint32_t s_bits[];
+    __shared__ int s_remaining;
+    __shared__ int s_cnt[COVER_THREADS];
+    BitVol bv;
+    bv.WX = bitvol_wx(g.X);
+    bv.w = use_smem ? s_bits : gbits;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = COVER_THREADS / 32;
+    if (threadIdx.x == 0) s_remaining = 0;
+    __syncthreads();
+    bitvol_init(g, bv, mask, &s_remaining);
+    __syncthreads();
+    for (int pi = 0; pi < n_pix; pi++) {
+        const int pix_th = pix_ths[pi];
+        for (int64_t r0 = 0; r0 < n; r0 += COVER_THREADS) {
+            if (s_remaining <= 0) break;
+            // phase A: parallel upper bounds
+            for (int i = w; i < COVER_THREADS; i += nw) {
+                int64_t r = r0 + i;
+                int cnt = -1;
+                if (r < n && !selected[r]) {
+                    int vc = order[r];
+                    int row = fgidx[vc];
+                    if (!(overlap != nullptr && overlap[vc]) && row >= 0) {   // :144
+                        int cz, cy, cx;
+                        vox_decode(g, vc, cz, cy, cx);
+                        cnt = patch_window_count<false>(g, bv, fcmask + (int64_t)row * g.W,
+                                                        cz, cy, cx, lane, nullptr);
+                    }
+                }
+                if (lane == 0) s_cnt[i] = cnt;
+            }
+            __syncthreads();
+            // phase B: serial replay of the survivors
+            if (w == 0) {
+                int remaining = s_remaining;
+                for (int i = 0; i < COVER_THREADS && remaining > 0; i++) {
+                    if (s_cnt[i] <= pix_th) continue;
+                    int64_t r = r0 + i;
+                    int vc = order[r];
+                    int cz, cy, cx;
+                    vox_decode(g, vc, cz, cy, cx);
+                    const uint32_t* pm = fcmask + (int64_t)fgidx[vc] * g.W;
+                    int cnt = patch_window_count<false>(g, bv, pm, cz, cy, cx, lane, nullptr);
+                    if (cnt > pix_th) {
+                        int rc = 0;
+                        patch_window_count<true>(g, bv, pm, cz, cy, cx, lane, &rc);
+                        __syncwarp();
+                        remaining -= warp_sum_i(rc);
+                        if (lane == 0) selected[r] = 1;
+                    }
+                }
+                if (lane == 0) s_remaining = remaining;
+            }
+            __syncthreads();
+        }
+        if (s_remaining < 1) break;                                  // :50-51
+    }
+}
+
+extern "C" int ppp_cover(const uint8_t* mask, const uint8_t* overlap, const int32_t* order,
+                         int64_t n, const int32_t* fgidx, const uint32_t* fcmask,
+                         const ppp_cfg* cfg, const int32_t* pix_ths, int32_t n_pix,
+                         uint8_t* selected, void* scratch, void* stream)
+{
+    if (n <= 0) return 0;
+    Geo g = make_geo(*cfg);
+    size_t bytes = (size_t)g.Z * g.Y * bitvol_wx(g.X) * 4;
+    int use_smem = bytes <= SMEM_BITVOL_MAX;
+    size_t smem = use_smem ? bytes : 0;
+    if (use_smem) {
+        cudaError_t e = cudaFuncSetAttribute(cover_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SMEM_BITVOL_MAX);
+        if (e != cudaSuccess) return ppp_fail((int)e, "ppp_cover: smem attribute");
+    }
+    cover_kernel<<<1, COVER_THREADS, smem, (cudaStream_t)stream>>>(
+        mask, overlap, order, n, fgidx, fcmask, *cfg, pix_ths, n_pix, selected,
+        (uint32_t*)scratch, use_smem);
+    return ppp_check("ppp_cover");
+}
+
+// ---------------------------------------------------------------------------
+// thinning = greedy set cover (foreground_cover.py:183-256, thin_cover_use_kd
+// False): repeatedly keep the patch that still covers the most uncovered
+// voxels (first maximum in list order, np.argmax), remove its voxels, until
+// the radslice is covered.  |S_i| after the reference's set subtraction equals
+// popc(patch bits & running mask), so only the patches whose window overlaps
+// the chosen one need re-counting.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(THIN_THREADS)
+thin_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__ sel, int64_t m,
+            const int32_t* __restrict__ fgidx, const uint32_t* __restrict__ fcmask,
+            ppp_cfg cfg, uint8_t* __restrict__ keep, uint32_t* gbits, int32_t* gcounts,
+            int use_smem)
+{
+    Geo g = make_geo(cfg);
+    extern __shared__ uint32_t s_bits[];
+    __shared__ int s_remaining;
+    __shared__ int s_best_cnt[THIN_THREADS / 32];
+    __shared__ int s_best_idx[THIN_THREADS / 32];
+    __shared__ int s_best;
+    BitVol bv;
+    bv.WX = bitvol_wx(g.X);
+    bv.w = use_smem ? s_bits : gbits;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = THIN_THREADS / 32;
+    if (threadIdx.x == 0) s_remaining = 0;
+    __syncthreads();
+    bitvol_init(g, bv, mask, &s_remaining);
+    for (int64_t i = threadIdx.x; i < m; i += blockDim.x) keep[i] = 0;
+    __syncthreads();
+    // initial |S_i|
+    for (int64_t i = w; i < m; i += nw) {
+        int vc = sel[i], row = fgidx[vc];
+        int cnt = 0;
+        if (row >= 0) {
+            int cz, cy, cx;
+            vox_decode(g, vc, cz, cy, cx);
+            cnt = patch_window_count<false>(g, bv, fcmask + (int64_t)row * g.W, cz, cy, cx,
+                                            lane, nullptr);
+        }
+        if (lane == 0) gcounts[i] = cnt;
+    }
+    __syncthreads();
+    while (s_remaining > 0) {
+        // first maximum
+        int bc = -1, bi = 0x7fffffff;
+        for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
+            int c = gcounts[i];
+            if (c > bc) { bc = c; bi = (int)i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oc > bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+        }
+        if (lane == 0) { s_best_cnt[w] = bc; s_best_idx[w] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int c = s_best_cnt[0], ix = s_best_idx[0];
+            for (int i = 1; i < nw; i++)
+                if (s_best_cnt[i] > c || (s_best_cnt[i] == c && s_best_idx[i] < ix)) {
+                    c = s_best_cnt[i]; ix = s_best_idx[i];
+                }
+            s_best = c > 0 ? ix : -1;   // nothing left that covers anything: stop
+        }
+        __syncthreads();
+        const int best = s_best;
+        if (best < 0) break;            // the reference would spin here
+        int bz, by, bx;
+        vox_decode(g, sel[best], bz, by, bx);
+        if (w == 0) {
+            int rc = 0;
+            patch_window_count<true>(g, bv, fcmask + (int64_t)fgidx[sel[best]] * g.W,
+                                     bz, by, bx, lane, &rc);
+            rc = warp_sum_i(rc);
+            if (lane == 0) { keep[best] = 1; s_remaining -= rc; gcounts[best] = 0; }
+        }
+        __syncthreads();
+        // re-count the patches whose window intersects the chosen one
+        for (int64_t i = w; i < m; i += nw) {
+            if (gcounts[i] == 0) continue;
+            int vc = sel[i];
+            int cz, cy, cx;
+            vox_decode(g, vc, cz, cy, cx);
+            if (abs(cz - bz) >= g.psz || abs(cy - by) >= g.psy || abs(cx - bx) >= g.psx) continue;
+            int row = fgidx[vc];
+            int cnt = patch_window_count<false>(g, bv, fcmask + (int64_t)row * g.W, cz, cy, cx,
+                                                lane, nullptr);
+            if (lane == 0) gcounts[i] = cnt;
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int64_t ppp_thin_scratch_bytes(const ppp_cfg* cfg, int64_t m)
+{
+    return ppp_cover_scratch_bytes(cfg) + 256 + 4 * (m > 0 ? m : 0);
+}
+
+extern "C" int ppp_thin(const uint8_t* mask, const int32_t* sel, int64_t m,
+                        const int32_t* fgidx, const uint32_t* fcmask, const ppp_cfg* cfg,
+                        uint8_t* keep, void* scratch, void* stream)
+{
+    if (m <= 0) return 0;
+    Geo g = make_geo(*cfg);
+    size_t bytes = (size_t)g.Z * g.Y * bitvol_wx(g.X) * 4;
+    int use_smem = bytes <= SMEM_BITVOL_MAX;
+    size_t smem = use_smem ? bytes : 0;
+    if (use_smem) {
+        cudaError_t e = cudaFuncSetAttribute(thin_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SMEM_BITVOL_MAX);
+        if (e != cudaSuccess) return ppp_fail((int)e, "ppp_thin: smem attribute");
+    }
+    // scratch: [bit volume][counts m]
+    uint32_t* gbits = (uint32_t*)scratch;
+    int32_t* gcounts = (int32_t*)((char*)scratch + ((bytes + 255) / 256) * 256);
+    thin_kernel<<<1, THIN_THREADS, smem, (cudaStream_t)stream>>>(
+        mask, sel, m, fgidx, fcmask, *cfg, keep, gbits, gcounts, use_smem);
+    return ppp_check("ppp_thin");
+}

@@ -1,0 +1,397 @@
+// Steps 5+6: patch affinity graph (computePatchGraph.cu:3-136), connected
+// components over positive edges and painting (aff_patch_graph.py:31-40,
+// graph_to_labeling.py:50-84).
+#include <cub/cub.cuh>
+#include "ppp_common.cuh"
+#include "ppp_api.cuh"
+
+// ---------------------------------------------------------------------------
+// patch graph.  The reference runs ONE THREAD per patch pair over all P x P
+// pixel pairs, 512 pairs per launch with a host sync in between
+// (aff_patch_graph.py:137-159).  Here one CTA owns a pair: the voting pixels of
+// both patches are compacted (in raster order) into shared memory and the
+// |L1| x |L2| products are spread over the threads.
+//
+// The 20 % sub-sampling inside the window intersection uses a serial LCG that
+// advances once per intersection pixel pair in loop order
+// (computePatchGraph.cu:75-86).  The k-th such pair (1-based) sees
+// rnd0 * a^k mod 2^32, and k = idx1 * n2 + idx2 + 1 with idx1 / idx2 the rank
+// of the pixel among the intersection pixels of its patch and n2 the number of
+// intersection pixels of patch 2, so every thread can jump to its state.
+// ---------------------------------------------------------------------------
+#define PG_THREADS 256
+#define LCG_A 1103515245u
+
+__device__ __forceinline__ uint32_t pow_u32(uint32_t a, uint32_t e)
+{
+    uint32_t r = 1u;
+    while (e) { if (e & 1u) r *= a; a *= a; e >>= 1; }
+    return r;
+}
+
+// ordered compaction of the voting pixels of patch (cz,cy,cx) into smem
+// (computePatchGraph.cu:41-52): pred[mid][p] > TH and pred[po][c] > TH.
+// Also ranks the pixels that lie inside the other patch's window.
+__device__ int pg_build_list(const Geo& g, const ppp_cfg& cfg, const float* __restrict__ pred,
+                             const uint8_t* __restrict__ flags, int cz, int cy, int cx,
+                             int oz, int oy, int ox,       // the other centre
+                             int16_t* s_po, int16_t* s_ii, int* s_scratch, int* n_inter)
+{
+    // s_scratch: [0..7] warp counts, [8..15] warp inter counts, [16] n, [17] n_inter
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t vc = ((int64_t)cz * g.Y + cy) * g.X + cx;
+    if (threadIdx.x == 0) { s_scratch[16] = 0; s_scratch[17] = 0; }
+    __syncthreads();
+    for (int base = 0; base < g.P; base += PG_THREADS) {
+        int po = base + threadIdx.x;
+        bool vote = false, inter = false;
+        if (po < g.P) {
+            int qz, qy, qx;
+            po_decode(g, po, qz, qy, qx);
+            int z = cz + qz - g.rz, y = cy + qy - g.ry, x = cx + qx - g.rx;
+            if (z >= 0 && z < g.Z && y >= 0 && y < g.Y && x >= 0 && x < g.X) {
+                int pv = (z * g.Y + y) * g.X + x;
+                vote = (flags[pv] & PPP_FLAG_FG) && pred[(int64_t)po * g.V + vc] > cfg.th_gt;
+                inter = vote && abs(x - ox) <= g.rx && abs(y - oy) <= g.ry && abs(z - oz) <= g.rz;
+            }
+        }
+        unsigned bv = __ballot_sync(0xffffffffu, vote);
+        unsigned bi = __ballot_sync(0xffffffffu, inter);
+        if (lane == 0) { s_scratch[w] = __popc(bv); s_scratch[8 + w] = __popc(bi); }
+        __syncthreads();
+        int off = s_scratch[16], offi = s_scratch[17];
+        for (int i = 0; i < w; i++) { off += s_scratch[i]; offi += s_scratch[8 + i]; }
+        if (vote) {
+            unsigned lt = (1u << lane) - 1u;
+            int idx = off + __popc(bv & lt);
+            s_po[idx] = (int16_t)po;
+            s_ii[idx] = inter ? (int16_t)(offi + __popc(bi & lt)) : (int16_t)-1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0, ti = 0;
+            for (int i = 0; i < PG_THREADS / 32; i++) { t += s_scratch[i]; ti += s_scratch[8 + i]; }
+            s_scratch[16] += t; s_scratch[17] += ti;
+        }
+        __syncthreads();
+    }
+    *n_inter = s_scratch[17];
+    return s_scratch[16];
+}
+
+__global__ void __launch_bounds__(PG_THREADS)
+patch_graph_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags,
+                   const int32_t* __restrict__ fgidx, const float* __restrict__ cons,
+                   const uint32_t* __restrict__ pairs, ppp_cfg cfg, float* __restrict__ aff)
+{
+    Geo g = make_geo(cfg);
+    extern __shared__ unsigned char smem_raw[];
+    int16_t* s_po1 = (int16_t*)smem_raw;          // [P]
+    int16_t* s_ii1 = s_po1 + g.P;                 // [P]
+    int16_t* s_po2 = s_ii1 + g.P;                 // [P]
+    int16_t* s_ii2 = s_po2 + g.P;                 // [P]
+    uint32_t* s_pw2 = (uint32_t*)(s_ii2 + g.P + (g.P & 1));   // [P] a^(ii2+1)
+    __shared__ int s_scr1[18], s_scr2[18];
+    __shared__ double s_red[PG_THREADS / 32];
+    __shared__ unsigned s_redc[PG_THREADS / 32];
+
+    const int64_t id = blockIdx.x;
+    const int z1c = pairs[id * 6], y1c = pairs[id * 6 + 1], x1c = pairs[id * 6 + 2];
+    const int z2c = pairs[id * 6 + 3], y2c = pairs[id * 6 + 4], x2c = pairs[id * 6 + 5];
+    const uint32_t rnd0 = (uint32_t)z1c * (uint32_t)z2c * (uint32_t)y1c * (uint32_t)y2c *
+                          (uint32_t)x1c * (uint32_t)x2c;
+    int ni1, ni2;
+    const int n1 = pg_build_list(g, cfg, pred, flags, z1c, y1c, x1c, z2c, y2c, x2c,
+                                 s_po1, s_ii1, s_scr1, &ni1);
+    const int n2 = pg_build_list(g, cfg, pred, flags, z2c, y2c, x2c, z1c, y1c, x1c,
+                                 s_po2, s_ii2, s_scr2, &ni2);
+    const uint32_t a_n2 = pow_u32(LCG_A, (uint32_t)ni2);     // a^(n2)
+    for (int j = threadIdx.x; j < n2; j += PG_THREADS)
+        s_pw2[j] = s_ii2[j] >= 0 ? pow_u32(LCG_A, (uint32_t)s_ii2[j] + 1u) : 0u;
+    __syncthreads();
+
+    double acc = 0.0;
+    unsigned cnt = 0;
+    for (int i = 0; i < n1; i++) {
+        int po1 = s_po1[i], ii1 = s_ii1[i];
+        int qz, qy, qx;
+        po_decode(g, po1, qz, qy, qx);
+        const int z1 = z1c + qz - g.rz, y1 = y1c + qy - g.ry, x1 = x1c + qx - g.rx;
+        const int64_t g1 = ((int64_t)z1 * g.Y + y1) * g.X + x1;
+        const int row1 = fgidx[g1];
+        const bool r1ok = row1 >= 0;
+        // LCG state before this row of the loop nest: rnd0 * a^(ii1*n2)
+        const uint32_t base_rnd = ii1 >= 0 ? rnd0 * pow_u32(a_n2, (uint32_t)ii1) : 0u;
+        for (int j = threadIdx.x; j < n2; j += PG_THREADS) {
+            int po2 = s_po2[j], ii2 = s_ii2[j];
+            int pz, py, px;
+            po_decode(g, po2, pz, py, px);
+            const int z2 = z2c + pz - g.rz, y2 = y2c + py - g.ry, x2 = x2c + px - g.rx;
+            if (ii1 >= 0 && ii2 >= 0) {
+                uint32_t rnd = base_rnd * s_pw2[j];
+                float rndT = (float)rnd / 4294967296.0f;
+                if ((double)rndT > 0.2) continue;
+            }
+            const int64_t g2 = ((int64_t)z2 * g.Y + y2) * g.X + x2;
+            int dz, dy, dx, rowb;
+            if (g1 <= g2) { dz = z2 - z1; dy = y2 - y1; dx = x2 - x1; rowb = row1; }
+            else { dz = z1 - z2; dy = y1 - y2; dx = x1 - x2; rowb = fgidx[g2]; }
+            // computePatchGraph.cu:98-101 / 116-119 (index = offset + ps - 1 in [0, 2ps))
+            if (dz < -(g.psz - 1) || dz > g.psz || dy < -(g.psy - 1) || dy > g.psy ||
+                dx < -(g.psx - 1) || dx > g.psx) continue;
+            cnt++;
+            int k = k_of_offset(g, dz, dy, dx);
+            if (k >= 0 && rowb >= 0 && (g1 <= g2 ? r1ok : true))
+                acc += (double)cons[(int64_t)rowb * g.K + k];
+        }
+    }
+    acc = warp_sum_d(acc);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { s_red[w] = acc; s_redc[w] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        unsigned c = 0;
+        for (int i = 0; i < PG_THREADS / 32; i++) { t += s_red[i]; c += s_redc[i]; }
+        float a = (float)t;
+        aff[id] = (cfg.graph_flags & 1) ? a / (float)(c > 1 ? c : 1) : a;
+    }
+}
+
+extern "C" int ppp_patch_graph(const float* pred, const uint8_t* flags,
+                               const int32_t* fgidx, const float* cons,
+                               const uint32_t* pairs, int64_t n, const ppp_cfg* cfg,
+                               float* aff, void* stream)
+{
+    if (n <= 0) return 0;
+    Geo g = make_geo(*cfg);
+    if (g.P > 32767) return ppp_fail(-1, "ppp_patch_graph: patch too large");
+    size_t smem = (size_t)g.P * 12 + 16;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(patch_graph_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return ppp_fail((int)e, "ppp_patch_graph: smem attribute");
+    }
+    patch_graph_kernel<<<(unsigned)n, PG_THREADS, smem, (cudaStream_t)stream>>>(
+        pred, flags, fgidx, cons, pairs, *cfg, aff);
+    return ppp_check("ppp_patch_graph");
+}
+
+// ---------------------------------------------------------------------------
+// connected components over edges with aff > 0, numbered in the reference's
+// order.  networkx yields components in node-insertion order of the positive
+// graph, which is built by iterating the edges of the full graph
+// (graph_to_labeling.py:50-54); a component therefore ranks by the smallest
+// first-appearance position (2*pair + endpoint, over pairs with aff != 0,
+// aff_patch_graph.py:35-39) among its nodes.  Lock-free union-find on the
+// voxel index of the patch centres.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(int32_t* parent, int v)
+{
+    int p = parent[v];
+    while (p != v) {
+        int gp = parent[p];
+        if (gp != p) parent[v] = gp;      // path halving (benign race)
+        v = p; p = gp;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void uf_union(int32_t* parent, int a, int b)
+{
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }      // hook larger root under smaller
+        int old = atomicCAS(&parent[a], a, b);
+        if (old == a) return;
+    }
+}
+
+__device__ __forceinline__ int pair_vox(const Geo& g, const uint32_t* pairs, int64_t i, int e)
+{
+    return (int)(((int64_t)pairs[i * 6 + 3 * e] * g.Y + pairs[i * 6 + 3 * e + 1]) * g.X +
+                 pairs[i * 6 + 3 * e + 2]);
+}
+
+__global__ void cc_init_kernel(const uint32_t* __restrict__ pairs, int64_t n, ppp_cfg cfg,
+                               int32_t* parent, int32_t* first, int32_t* key, int32_t* comp)
+{
+    Geo g = make_geo(cfg);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int e = 0; e < 2; e++) {
+        int v = pair_vox(g, pairs, i, e);
+        parent[v] = v; first[v] = 0x7fffffff; key[v] = 0x7fffffff; comp[v] = 0;
+    }
+}
+
+__global__ void cc_union_kernel(const uint32_t* __restrict__ pairs, const float* __restrict__ aff,
+                                int64_t n, ppp_cfg cfg, int32_t* parent, int32_t* first)
+{
+    Geo g = make_geo(cfg);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = aff[i];
+    if (a == 0.0f) return;                           // aff_patch_graph.py:36
+    int v0 = pair_vox(g, pairs, i, 0), v1 = pair_vox(g, pairs, i, 1);
+    atomicMin(&first[v0], (int)(2 * i));
+    atomicMin(&first[v1], (int)(2 * i + 1));
+    if (a > 0.0f) uf_union(parent, v0, v1);          // graph_to_labeling.py:52
+}
+
+// key[root] = min first-appearance over the members that have a positive edge
+__global__ void cc_key_kernel(const uint32_t* __restrict__ pairs, const float* __restrict__ aff,
+                              int64_t n, ppp_cfg cfg, int32_t* parent, const int32_t* first,
+                              int32_t* key)
+{
+    Geo g = make_geo(cfg);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!(aff[i] > 0.0f)) return;
+    for (int e = 0; e < 2; e++) {
+        int v = pair_vox(g, pairs, i, e);
+        int r = uf_find(parent, v);
+        atomicMin(&key[r], first[v]);
+    }
+}
+
+// collect each root once: (key, root)
+__global__ void cc_roots_kernel(const uint32_t* __restrict__ pairs, const float* __restrict__ aff,
+                                int64_t n, ppp_cfg cfg, int32_t* parent, int32_t* key,
+                                int32_t* comp, uint64_t* roots, int32_t* n_comp)
+{
+    Geo g = make_geo(cfg);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!(aff[i] > 0.0f)) return;
+    int v = pair_vox(g, pairs, i, 0);
+    int r = uf_find(parent, v);
+    if (atomicExch(&comp[r], -1) == 0) {            // first visitor claims the root
+        int slot = atomicAdd(n_comp, 1);
+        roots[slot] = ((uint64_t)(uint32_t)key[r] << 32) | (uint32_t)r;
+    }
+}
+
+__global__ void cc_number_kernel(const uint64_t* __restrict__ roots_sorted, int n_roots,
+                                 int32_t* comp)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_roots) return;
+    comp[(uint32_t)(roots_sorted[i] & 0xffffffffu)] = -(i + 1) - 1;   // tagged: -(k+1)
+}
+
+__global__ void cc_assign_kernel(const uint32_t* __restrict__ pairs, const float* __restrict__ aff,
+                                 int64_t n, ppp_cfg cfg, int32_t* parent, int32_t* comp)
+{
+    Geo g = make_geo(cfg);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!(aff[i] > 0.0f)) return;
+    for (int e = 0; e < 2; e++) {
+        int v = pair_vox(g, pairs, i, e);
+        int r = uf_find(parent, v);
+        if (r != v) comp[v] = -comp[r] - 1;         // roots keep the tagged value for now
+    }
+}
+
+__global__ void cc_untag_kernel(const uint64_t* __restrict__ roots_sorted, int n_roots,
+                                int32_t* comp)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_roots) return;
+    comp[(uint32_t)(roots_sorted[i] & 0xffffffffu)] = i + 1;
+}
+
+static size_t roots_sort_bytes(int64_t n)
+{
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortKeys((void*)nullptr, tb, (const uint64_t*)nullptr,
+                                   (uint64_t*)nullptr, (int)(n > 0 ? n : 1));
+    return tb;
+}
+
+extern "C" int64_t ppp_label_scratch_bytes(int64_t V, int64_t n)
+{
+    size_t tb = roots_sort_bytes(n);
+    return (int64_t)(3 * ((V * 4 + 255) / 256) * 256 + 2 * ((n * 8 + 255) / 256 + 1) * 256 +
+                     ((tb + 255) / 256) * 256 + 256);
+}
+
+extern "C" int ppp_label_cc(const uint32_t* pairs, const float* aff, int64_t n,
+                            const ppp_cfg* cfg, int32_t* comp, int32_t* n_comp,
+                            void* scratch, void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(n_comp, 0, sizeof(int32_t), s);
+    if (n <= 0) return ppp_check("ppp_label_cc");
+    Geo g = make_geo(*cfg);
+    size_t vb = ((g.V * 4 + 255) / 256) * 256;
+    size_t rb = ((n * 8 + 255) / 256 + 1) * 256;
+    char* base = (char*)scratch;
+    int32_t* parent = (int32_t*)base;
+    int32_t* first = (int32_t*)(base + vb);
+    int32_t* key = (int32_t*)(base + 2 * vb);
+    uint64_t* roots = (uint64_t*)(base + 3 * vb);
+    uint64_t* roots_sorted = (uint64_t*)(base + 3 * vb + rb);
+    void* sort_tmp = base + 3 * vb + 2 * rb;
+    size_t tb = roots_sort_bytes(n);
+    unsigned nb = (unsigned)((n + 255) / 256);
+    cc_init_kernel<<<nb, 256, 0, s>>>(pairs, n, *cfg, parent, first, key, comp);
+    cc_union_kernel<<<nb, 256, 0, s>>>(pairs, aff, n, *cfg, parent, first);
+    cc_key_kernel<<<nb, 256, 0, s>>>(pairs, aff, n, *cfg, parent, first, key);
+    cc_roots_kernel<<<nb, 256, 0, s>>>(pairs, aff, n, *cfg, parent, key, comp, roots, n_comp);
+    // the number of roots is only known on the device; sort the full buffer
+    // after padding it with +inf keys
+    // (n is small: pairs of selected patches)
+    cudaMemsetAsync(roots_sorted, 0xff, n * 8, s);
+    int32_t h_ncomp = 0;
+    cudaMemcpyAsync(&h_ncomp, n_comp, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    if (h_ncomp > 0) {
+        cub::DeviceRadixSort::SortKeys(sort_tmp, tb, roots, roots_sorted, h_ncomp, 0, 64, s);
+        unsigned rbk = (unsigned)((h_ncomp + 255) / 256);
+        cc_number_kernel<<<rbk, 256, 0, s>>>(roots_sorted, h_ncomp, comp);
+        cc_assign_kernel<<<nb, 256, 0, s>>>(pairs, aff, n, *cfg, parent, comp);
+        cc_untag_kernel<<<rbk, 256, 0, s>>>(roots_sorted, h_ncomp, comp);
+    }
+    return ppp_check("ppp_label_cc");
+}
+
+// ---------------------------------------------------------------------------
+// painting (graph_to_labeling.py:68-84): every pixel of a member patch with
+// pred > patch_threshold takes the component number; later components
+// overwrite earlier ones == the maximum wins.
+// ---------------------------------------------------------------------------
+__global__ void paint_kernel(const float* __restrict__ pred, const int32_t* __restrict__ nodes,
+                             const int32_t* __restrict__ comp, ppp_cfg cfg,
+                             int32_t* __restrict__ instances)
+{
+    Geo g = make_geo(cfg);
+    const int vc = nodes[blockIdx.x];
+    const int c = comp[vc];
+    if (c <= 0) return;
+    int cz, cy, cx;
+    vox_decode(g, vc, cz, cy, cx);
+    for (int po = threadIdx.x; po < g.P; po += blockDim.x) {
+        int qz, qy, qx;
+        po_decode(g, po, qz, qy, qx);
+        int z = cz + qz - g.rz, y = cy + qy - g.ry, x = cx + qx - g.rx;
+        if (z < 0 || z >= g.Z || y < 0 || y >= g.Y || x < 0 || x >= g.X) continue;
+        if (pred[(int64_t)po * g.V + vc] > cfg.pt_gt)
+            atomicMax(&instances[(z * g.Y + y) * g.X + x], c);
+    }
+}
+
+extern "C" int ppp_paint(const float* pred, const int32_t* nodes, int64_t m,
+                         const int32_t* comp, const ppp_cfg* cfg, int32_t* instances,
+                         void* stream)
+{
+    if (m <= 0) return 0;
+    paint_kernel<<<(unsigned)m, 128, 0, (cudaStream_t)stream>>>(pred, nodes, comp, *cfg,
+                                                                 instances);
+    return ppp_check("ppp_paint");
+}

@@ -1,0 +1,243 @@
+// Step 0 of instance assembly on the device: foreground gate, row compaction
+// and the centre-major class-folded patch array.  Replaces the host-side
+// np.where / list-comprehension filtering of vote_instances.py:276-287 and the
+// per-thread re-reading of thresholds in every reference kernel.
+#include "ppp_common.cuh"
+#include "ppp_api.cuh"
+
+// ---------------------------------------------------------------------------
+// gate: flags[v] = FG | GATED | CENTRE  (fillConsensusArray.cu:25-33, 53-60)
+// ---------------------------------------------------------------------------
+__global__ void gate_kernel(const float* __restrict__ pred_mid,
+                            const uint8_t* __restrict__ overlap,
+                            const uint8_t* __restrict__ cand,
+                            ppp_cfg cfg, uint8_t* __restrict__ flags)
+{
+    Geo g = make_geo(cfg);
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= g.V) return;
+    int z, y, x;
+    vox_decode(g, (int)v, z, y, x);
+    bool fg = pred_mid[v] > cfg.th_gt;
+    bool ov = cfg.use_overlap && overlap != nullptr && overlap[v] != 0;
+    bool interior = x >= g.rx && x < g.X - g.rx && y >= g.ry && y < g.Y - g.ry &&
+                    z >= g.rz && z < g.Z - g.rz;
+    uint8_t f = interior ? PPP_FLAG_INTERIOR : 0;
+    if (cand != nullptr && cand[v] != 0) f |= PPP_FLAG_CAND;
+    if (fg) {
+        f |= PPP_FLAG_FG;
+        if (!ov) f |= PPP_FLAG_GATED;
+        if (interior) f |= PPP_FLAG_CENTRE;
+    }
+    flags[v] = f;
+}
+
+extern "C" int ppp_gate(const float* pred, const uint8_t* overlap, const uint8_t* cand,
+                        const ppp_cfg* cfg, uint8_t* flags, void* stream)
+{
+    Geo g = make_geo(*cfg);
+    if (g.V <= 0 || g.V > 0x7fffffffLL) return ppp_fail(-1, "ppp_gate: bad volume size");
+    int mid = g.P / 2;
+    int threads = 256;
+    int64_t blocks = (g.V + threads - 1) / threads;
+    gate_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        pred + (int64_t)mid * g.V, overlap, cand, *cfg, flags);
+    return ppp_check("ppp_gate");
+}
+
+// ---------------------------------------------------------------------------
+// compaction: three-phase exclusive scan over (flags & FG)
+// ---------------------------------------------------------------------------
+#define SCAN_ITEMS 2048     // voxels per block (256 threads x 8)
+
+__global__ void scan_count_kernel(const uint8_t* __restrict__ flags, int64_t V,
+                                  int32_t* __restrict__ block_counts)
+{
+    int64_t base = (int64_t)blockIdx.x * SCAN_ITEMS;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < SCAN_ITEMS; i += blockDim.x) {
+        int64_t v = base + i;
+        if (v < V) cnt += (flags[v] & PPP_FLAG_ROW) ? 1 : 0;
+    }
+    __shared__ int ws[8];
+    cnt = warp_sum_i(cnt);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) s += ws[i];
+        block_counts[blockIdx.x] = s;
+    }
+}
+
+// single block: exclusive scan of block_counts in place, total -> n_rows
+__global__ void scan_blocks_kernel(int32_t* __restrict__ block_counts, int nb,
+                                   int64_t* __restrict__ n_rows)
+{
+    __shared__ int ws[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int val = i < nb ? block_counts[i] : 0;
+        int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        int inc = val;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) ws[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            int t = lane < (int)(blockDim.x >> 5) ? ws[lane] : 0;
+            int ti = t;
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, ti, o);
+                if (lane >= o) ti += u;
+            }
+            ws[lane] = ti - t;       // exclusive warp offsets
+        }
+        __syncthreads();
+        int carry = carry_s;
+        int excl = carry + ws[w] + inc - val;
+        if (i < nb) block_counts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = excl + val;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_rows = carry_s;
+}
+
+__global__ void scan_write_kernel(const uint8_t* __restrict__ flags, int64_t V,
+                                  const int32_t* __restrict__ block_offsets,
+                                  int32_t* __restrict__ fgidx,
+                                  int32_t* __restrict__ rowvox)
+{
+    // each thread owns 8 consecutive voxels so that rows stay in raster order
+    __shared__ int ws[8];
+    int64_t base = (int64_t)blockIdx.x * SCAN_ITEMS + (int64_t)threadIdx.x * 8;
+    int f[8];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int64_t v = base + i;
+        f[i] = (v < V && (flags[v] & PPP_FLAG_ROW)) ? 1 : 0;
+        cnt += f[i];
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int i = 0; i < w; i++) woff += ws[i];
+    int row = block_offsets[blockIdx.x] + woff + inc - cnt;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int64_t v = base + i;
+        if (v < V) {
+            if (f[i]) { fgidx[v] = row; rowvox[row] = (int32_t)v; row++; }
+            else fgidx[v] = -1;
+        }
+    }
+}
+
+extern "C" int64_t ppp_compact_scratch_bytes(int64_t V)
+{
+    int64_t nb = (V + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    return (nb + 1) * (int64_t)sizeof(int32_t);
+}
+
+extern "C" int ppp_compact(const uint8_t* flags, int64_t V, int32_t* fgidx,
+                           int32_t* rowvox, int64_t* n_rows, void* scratch,
+                           void* stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t nb = (V + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    int32_t* bc = (int32_t*)scratch;
+    scan_count_kernel<<<(unsigned)nb, 256, 0, s>>>(flags, V, bc);
+    scan_blocks_kernel<<<1, 1024, 0, s>>>(bc, (int)nb, n_rows);
+    scan_write_kernel<<<(unsigned)nb, 256, 0, s>>>(flags, V, bc, fgidx, rowvox);
+    return ppp_check("ppp_compact");
+}
+
+// ---------------------------------------------------------------------------
+// prepare: dense [P][V] planes -> centre-major rows through a 32x32 transpose
+// tile, so that the plane reads (fixed po, consecutive centres) and the row
+// writes (fixed centre, consecutive po) are both coalesced.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prepare_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags,
+               const int32_t* __restrict__ rowvox, int64_t F, ppp_cfg cfg,
+               float* __restrict__ dp, uint32_t* __restrict__ fcmask,
+               uint32_t* __restrict__ ptmask)
+{
+    Geo g = make_geo(cfg);
+    __shared__ float tileD[32][33];
+    __shared__ uint8_t tileB[32][36];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * 32;
+    const int po0 = blockIdx.y * 32;
+
+    // phase 1: lane <-> centre row, warp <-> po
+    int64_t row = row0 + lane;
+    int v = -1, z = 0, y = 0, x = 0;
+    bool centre = false, interior = false;
+    if (row < F) {
+        v = rowvox[row];
+        vox_decode(g, v, z, y, x);
+        centre = (flags[v] & PPP_FLAG_CENTRE) != 0;
+        interior = (flags[v] & PPP_FLAG_INTERIOR) != 0;
+    }
+    for (int pl = w; pl < 32; pl += 8) {
+        int po = po0 + pl;
+        float d = 0.0f;
+        uint8_t b = 0;
+        if (interior && po < g.P) {
+            float val = pred[(int64_t)po * g.V + v];
+            if (centre) {
+                int qz, qy, qx;
+                po_decode(g, po, qz, qy, qx);
+                int pv = ((z + qz - g.rz) * g.Y + (y + qy - g.ry)) * g.X + (x + qx - g.rx);
+                if (flags[pv] & PPP_FLAG_GATED) d = fold_class(val, cfg.th_gt, cfg.bg_lt);
+            }
+            b = (val > cfg.fc_gt ? 1 : 0) | (val > cfg.pt_gt ? 2 : 0);
+        }
+        tileD[pl][lane] = d;
+        tileB[pl][lane] = b;
+    }
+    __syncthreads();
+    // phase 2: lane <-> po, warp <-> 4 rows
+    for (int rl = w; rl < 32; rl += 8) {
+        int64_t r = row0 + rl;
+        if (r >= F) break;
+        int po = po0 + lane;
+        float d = tileD[lane][rl];
+        uint8_t b = tileB[lane][rl];
+        if (dp != nullptr && po < g.P) dp[r * g.P + po] = d;
+        unsigned m1 = __ballot_sync(0xffffffffu, b & 1);
+        unsigned m2 = __ballot_sync(0xffffffffu, b & 2);
+        if (lane == 0) {
+            if (fcmask != nullptr) fcmask[r * g.W + blockIdx.y] = m1;
+            if (ptmask != nullptr) ptmask[r * g.W + blockIdx.y] = m2;
+        }
+    }
+}
+
+extern "C" int ppp_prepare_patches(const float* pred, const uint8_t* flags,
+                                   const int32_t* rowvox, int64_t F,
+                                   const ppp_cfg* cfg, float* dp,
+                                   uint32_t* fcmask, uint32_t* ptmask,
+                                   void* stream)
+{
+    if (F <= 0) return 0;
+    Geo g = make_geo(*cfg);
+    dim3 grid((unsigned)((F + 31) / 32), (unsigned)g.W);
+    prepare_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        pred, flags, rowvox, F, *cfg, dp, fcmask, ptmask);
+    return ppp_check("ppp_prepare_patches");
+}

@@ -1,0 +1,269 @@
+"""Drop-in for PatchPerPix/vote_instances/vote_instances.py on the B200 path.
+
+Same entry points and keyword surface as the reference:
+    main(**kwargs)                                   vote_instances.py:557
+    do_all(aff_file, patchshape, **kwargs)           vote_instances.py:486
+    do_block(block, foreground, mask, numinst, **kw) vote_instances.py:455
+    to_instance_seg(pred_affs, foreground, mask_to_cover, numinst,
+                    patchshape, **kwargs)            vote_instances.py:150
+but steps (1)-(6) run on the GPU through include/ppp_b200.h
+(patchperpix_b200/assembly.py).  `cuda=False` is refused: this build has no
+CPU path.  Arrays may be numpy (copied to the device here — that copy is part
+of the end-to-end cost), pinned torch CPU tensors or CUDA tensors.
+"""
+import glob
+import logging
+import os
+
+import numpy as np
+
+from . import cuda_code
+from .assembly import BlockAssembler
+from .utilVoteInstances import loadAffinities, getResKey
+
+logger = logging.getLogger(__name__)
+
+_UNSUPPORTED = ('isbiHack', 'debug', 'graphToInst', 'use_score_oracle',
+                'mark_close_neighboorhood', 'select_patches_overlap_neighborhood',
+                'thin_cover_use_kd', 'one_instance_per_channel',
+                'no_overlap_per_channel', 'shuffle_patches')
+
+
+def merge_dicts(sink, source):
+    """vote_instances.py:49-59."""
+    if not isinstance(sink, dict) or not isinstance(source, dict):
+        raise TypeError('Args to merge_dicts should be dicts')
+    for k, v in source.items():
+        if isinstance(source[k], dict) and isinstance(sink.get(k), dict):
+            sink[k] = merge_dicts(sink[k], v)
+        else:
+            sink[k] = v
+    return sink
+
+
+def _to_device(a, dtype=None):
+    import torch
+    if isinstance(a, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    else:
+        t = a
+    if t.dtype == torch.bool:
+        t = t.to(torch.uint8)
+    t = t.cuda(non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
+                    **kwargs):
+    """vote_instances.py:150-452.  Returns (instances u16, foreground u8), or
+    (pairs u32 [n,6], aff f32 [n]) with return_intermediates, all numpy."""
+    import torch
+    if not kwargs.get('cuda', True):
+        raise NotImplementedError(
+            "patchperpix_b200 only provides the CUDA path (cuda=True)")
+    for k in _UNSUPPORTED:
+        if kwargs.get(k, False):
+            raise NotImplementedError("vote_instances option %r is outside "
+                                      "the B200 hot path" % k)
+    if kwargs.get('mws', False) and not kwargs.get('return_intermediates', False):
+        raise NotImplementedError("mws labelling is a later row of the scope "
+                                  "table; use mws=False (thresholded CC)")
+    patchshape = np.array(patchshape)
+    rad = np.array([p // 2 for p in patchshape])
+    ret_inter = kwargs.get('return_intermediates', False)
+
+    fg_np_in = foreground
+    pred = _to_device(pred_affs, torch.float32)
+    fg = _to_device(foreground, torch.uint8)
+    mask = _to_device(mask_to_cover, torch.uint8).clone()
+    numinst_t = _to_device(numinst)
+    if kwargs.get("pad_with_ps", False):                       # :166-190
+        assert not kwargs.get('blockwise', False), "can only pad whole volumes"
+        pad = (int(rad[2]),) * 2 + (int(rad[1]),) * 2 + (int(rad[0]),) * 2
+        pred = torch.nn.functional.pad(pred, pad).contiguous()
+        fg = torch.nn.functional.pad(fg, pad).contiguous()
+        mask = torch.nn.functional.pad(mask, pad).contiguous()
+        numinst_t = torch.nn.functional.pad(numinst_t, pad).contiguous()
+    shape = tuple(int(s) for s in fg.shape)
+    overlap = (numinst_t > 1).to(torch.uint8)                  # :211
+    if not kwargs.get('blockwise', False) and kwargs.get('skeletonize_foreground'):
+        raise NotImplementedError("skeletonize_foreground needs skimage "
+                                  "(non-blockwise only, vote_instances.py:220-224)")
+    mask[overlap > 0] = 0                                      # :226
+    radslice = tuple(slice(int(rad[i]), shape[i] - int(rad[i])) for i in range(3))
+
+    def _unpad(t):
+        if kwargs.get("pad_with_ps", False):
+            return t[radslice]
+        return t
+
+    def _empty_result():
+        if ret_inter:
+            return None, None
+        inst = torch.zeros(shape, dtype=torch.int32, device=pred.device)
+        return (_unpad(inst).cpu().numpy().astype(np.uint16),
+                _unpad(fg).cpu().numpy().astype(np.uint8))
+
+    if int(torch.count_nonzero(mask[radslice]).item()) == 0:   # :232-245
+        logger.info("no fg found, returning...")
+        return _empty_result()
+
+    asm = BlockAssembler(pred, fg, overlap, patchshape, **kwargs)
+    asm.prepare()
+    cand = asm.candidates()                                    # :276-287
+    if cand.numel() == 0:
+        logger.info("no patches found, returning...")
+        return _empty_result()
+
+    # (1) consensus
+    if not kwargs.get('skipConsensus', False):
+        asm.consensus()
+    if kwargs.get('save_consensus', False):
+        return None, None
+    # (2) ranking
+    order = None
+    if not kwargs.get('skipRanking', False):
+        asm.rank()
+        order = asm.ranked(cand)
+        logger.info("num ranked patches %s", int(order.numel()))
+
+    if kwargs.get('aff_graph') is not None:
+        raise NotImplementedError("loading a stored patch graph")
+    # (3)/(4) selection
+    if kwargs.get('selected_patches') is not None:             # :369-375
+        sc = np.asarray(kwargs['selected_patches'], dtype=np.int64).reshape(-1, 3)
+        sel_coords = sc
+    else:
+        if kwargs.get('skipSelection', False):
+            sel = order
+        else:
+            sel = asm.cover(mask, order)
+        if not kwargs.get('skipThinCover', False) and sel.numel() > 0:
+            sel = asm.thin(mask, sel)
+        sel_coords = asm.coords(sel)
+    # (4b) pairs
+    if kwargs.get('selected_patch_pairs') is not None:         # :400-406
+        pairs = np.array(kwargs['selected_patch_pairs'], dtype=np.uint32).reshape(-1, 6)
+        if len(pairs) == 0:
+            pairs = None
+    else:
+        pairs = asm.patch_pairs(sel_coords)
+    if pairs is None:                                          # :413-417
+        return _empty_result()
+    if kwargs.get('termAfterThinCover', False):
+        return None, None
+    # (5) patch graph
+    pairs_dev = torch.from_numpy(pairs.view(np.int32)).to(pred.device)
+    aff = asm.patch_graph(pairs_dev)
+    if kwargs.get("save_patch_graph", False) or kwargs.get("termAfterPatchGraph", False):
+        fn = os.path.splitext(os.path.basename(kwargs.get('affinities', 'block')))[0]
+        np.save(os.path.join(kwargs['result_folder'], fn + "_selected_patch_pairs.npy"), pairs)
+        np.save(os.path.join(kwargs['result_folder'], fn + "_aff_graph.npy"),
+                aff.cpu().numpy())
+    if ret_inter:
+        return pairs, aff.cpu().numpy()
+    if kwargs.get('termAfterPatchGraph', False):
+        return None, None
+    # (6) labelling
+    Y, X = shape[1], shape[2]
+    nodes_np = np.unique(np.concatenate([
+        (pairs[:, 0].astype(np.int64) * Y + pairs[:, 1]) * X + pairs[:, 2],
+        (pairs[:, 3].astype(np.int64) * Y + pairs[:, 4]) * X + pairs[:, 5]]))
+    nodes = torch.from_numpy(nodes_np.astype(np.int32)).to(pred.device)
+    inst, ncomp = asm.label(pairs_dev, aff, nodes)
+    if ncomp > 65535:
+        logger.warning("%d components do not fit the reference's uint16 labels", ncomp)
+    inst = _unpad(inst)
+    return (inst.cpu().numpy().astype(np.uint16),
+            _unpad(fg).cpu().numpy().astype(np.uint8))
+
+
+def do_block(block, foreground, mask, numinst, **kwargs):
+    """vote_instances.py:455-483."""
+    patchshape = kwargs['patchshape']
+    del kwargs['patchshape']
+    if type(patchshape) != np.ndarray:
+        patchshape = np.array(patchshape)
+    res = to_instance_seg(block, foreground, mask, numinst, patchshape, **kwargs)
+    if kwargs.get('return_intermediates'):
+        return res
+    instances, _ = res
+    rad = np.array([p // 2 for p in patchshape])
+    slices = tuple(slice(r, d - r) for r, d in zip(rad, instances.shape))
+    return instances[slices]
+
+
+def do_all(aff_file, patchshape=np.array([1, 25, 25]), **kwargs):
+    """vote_instances.py:486-554: load -> assemble -> write <sample>.hdf/.npz."""
+    logger.info("processing %s into %s", aff_file, kwargs['result_folder'])
+    if type(patchshape) is not np.ndarray:
+        patchshape = np.array(patchshape)
+    res_ext = getResKey(**kwargs) if kwargs.get('add_suffix', False) else ''
+    loaded = loadAffinities(aff_file, res_ext, patchshape=patchshape, **kwargs)
+    if loaded is None:
+        return
+    affinities, numinst, foreground = loaded
+    mask = np.copy(foreground)
+    if numinst is None:
+        numinst = np.copy(foreground)
+    kwargs['aff_file'] = aff_file
+    res = to_instance_seg(affinities, foreground, mask, numinst, patchshape, **kwargs)
+    res_key = kwargs.get('res_key', 'vote_instances')
+    instances, foreground = res
+    if instances is None and foreground is None:
+        return
+    foreground = foreground.astype(np.uint8)
+    if kwargs.get('crop_to_foreground', True):                 # :535-540
+        instances[foreground == 0] = 0
+    fn = os.path.splitext(os.path.basename(aff_file))[0]
+    from .io_util import write_result
+    write_result(os.path.join(kwargs['result_folder'], fn),
+                 {res_key + res_ext: instances,
+                  'vote_foreground' + res_ext: foreground},
+                 kwargs.get('output_format', 'hdf'))
+
+
+def main(**kwargs):
+    """vote_instances.py:557-605 (without re-parsing sys.argv)."""
+    args = dict(affinities=None, affinities_key="images/pred_affs", basedir=None,
+                mode=None, checkpoint=None, debug=False, patch_threshold=0.9,
+                fc_threshold=0.5, consensus=None, scores=None, ranked_patches=None,
+                aff_graph=None, selected_patches=None, selected_patch_pairs=None,
+                select_patches_for_sparse_data=False, cuda=False, skipLookup=False,
+                skipThinCover=False, skipRanking=False, skipConsensus=False,
+                termAfterThinCover=False, graphToInst=False, mws=False,
+                includeSinglePatchCCS=False, removeIntersection=False,
+                isbiHack=False, mask_fg_border=False, parallel=False,
+                save_no_intermediates=False)       # argparse defaults, :62-147
+    if len(kwargs) > 0:
+        args = merge_dicts(args, kwargs)
+    if 'check_required' in kwargs:
+        assert type(args.get('patchshape')) in [np.ndarray, tuple, list], \
+            "Please check type of patchshape {}".format(type(args.get('patchshape')))
+        assert type(args.get('result_folder')) == str, \
+            "Please check type of result_folder {}".format(type(args.get('result_folder')))
+    if args.get('cuda') and not args.get('graphToInst', False):
+        args['context'] = cuda_code.init_cuda()
+    os.makedirs(args['result_folder'], exist_ok=True)
+    affinities = args['affinities']
+    if affinities is not None:
+        if affinities.endswith(".zarr") or os.path.isfile(affinities):
+            do_all(affinities, **args)
+            return
+        elif os.path.isdir(affinities):
+            aff_files = glob.glob(os.path.join(affinities, "*.hdf")) + \
+                glob.glob(os.path.join(affinities, "*.npy"))
+        else:
+            raise RuntimeError("affinities (%s) should be file or dir", affinities)
+    else:
+        aff_files = []
+        if args['mode'] is not None and args['checkpoint'] is not None:
+            aff_files = glob.glob(os.path.join(args['basedir'], args['mode'],
+                                               "processed", args['checkpoint'], "*.hdf"))
+    if args['parallel']:
+        raise NotImplementedError
+    for fl in aff_files:
+        do_all(fl, **args)
+    cuda_code.delete_cuda(args.get('context'))
