@@ -201,6 +201,7 @@ void ppp_oracle_rank(const ppp_oracle_cfg* c, const float* pred,
         }
         if (pm[vc] <= TH) continue;          /* keeps the zero-init value */
         float acc = 0.0f;
+        double dacc = 0.0;      /* flags bit2: exact-ish sum, diagnostic only */
         unsigned fgCnt = 0;
         for (int pz1 = 0; pz1 < PSZ; pz1++)
         for (int py1 = 0; py1 < PSY; py1++)
@@ -226,6 +227,7 @@ void ppp_oracle_rank(const ppp_oracle_cfg* c, const float* pred,
                     if (po2 <= po1) continue;
                     float v3 = cons_at(c, cons, fgidx, K, v1i,
                                        pz2 - pz1, py2 - py1, px2 - px1);
+                    dacc += v3;
                     if (flags & 2) {
                         if (v3 != 0) acc += copysignf(1, v3);
                         else acc -= 1;
@@ -238,6 +240,7 @@ void ppp_oracle_rank(const ppp_oracle_cfg* c, const float* pred,
                     else
                         v3 = cons_at(c, cons, fgidx, K, v1i,
                                      pz2 - pz1, py2 - py1, px2 - px1);
+                    dacc -= v3;
                     if (flags & 2) {
                         if (v3 != 0) acc -= copysignf(1, v3);
                         else acc -= 1;
@@ -246,6 +249,7 @@ void ppp_oracle_rank(const ppp_oracle_cfg* c, const float* pred,
                 fgCnt += 1;
             }
         }
+        if (flags & 4) acc = (float)dacc;
         if (flags & 1) score[vc] = acc / (float)(fgCnt > 1 ? fgCnt : 1);
         else score[vc] = acc;
     }

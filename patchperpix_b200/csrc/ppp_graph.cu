@@ -90,7 +90,7 @@ patch_graph_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ f
     int16_t* s_ii1 = s_po1 + g.P;                 // [P]
     int16_t* s_po2 = s_ii1 + g.P;                 // [P]
     int16_t* s_ii2 = s_po2 + g.P;                 // [P]
-    uint32_t* s_pw2 = (uint32_t*)(s_ii2 + g.P + (g.P & 1));   // [P] a^(ii2+1)
+    uint32_t* s_pw2 = (uint32_t*)(s_ii2 + g.P);              // [P] a^(ii2+1)
     __shared__ int s_scr1[18], s_scr2[18];
     __shared__ double s_red[PG_THREADS / 32];
     __shared__ unsigned s_redc[PG_THREADS / 32];
