@@ -89,17 +89,25 @@ int ppp_compact(const uint8_t* flags, int64_t V, int32_t* fgidx, int32_t* rowvox
 /* ---- step 0b: centre-major class-folded patches + bit masks --------------
  * dp f32 [F][P]; fcmask/ptmask u32 [F][W], W = (P+31)/32: bit po set iff
  * pred[po][c] > fc_gt / > pt_gt (foreground_cover.py:158, graph_to_labeling.py:84).
+ * rbits u64 [F][psz*psy][2]: "received" class bits of every gated voxel — bit
+ * (dx + rx) of word (dz,dy) says the centre at b + d calls b high (word 0) /
+ * background (word 1); the vote counters are popcounts over them.
  * Any output pointer may be NULL. */
 int ppp_prepare_patches(const float* pred, const uint8_t* flags,
                         const int32_t* rowvox, int64_t F, const ppp_cfg* cfg,
                         float* dp, uint32_t* fcmask, uint32_t* ptmask,
-                        void* stream);
+                        uint64_t* rbits, void* stream);
 
 /* ---- step 1: consensus (fillConsensusArray.cu + normConsensusArray.cu) ----
- * cons f32 [F][K] (normalised iff cfg->norm_aff), cnt u32 [F][K] or NULL. */
-int ppp_consensus(const float* dp, const uint8_t* flags, const int32_t* fgidx,
-                  const int32_t* rowvox, int64_t F, const ppp_cfg* cfg,
-                  float* cons, uint32_t* cnt, void* stream);
+ * cons f32 [F][K] (normalised iff cfg->norm_aff), cnt u32 [F][K].
+ * impl: 0 = tiled (vote counters from `rbits`, sums from shared-memory tiles;
+ * needs rbits and scratch of ppp_consensus_scratch_bytes(cfg)), 1 = the simple
+ * one-CTA-per-voxel gather kept as a cross-check (rbits/scratch/cnt may be NULL). */
+int64_t ppp_consensus_scratch_bytes(const ppp_cfg* cfg);
+int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8_t* flags,
+                  const int32_t* fgidx, const int32_t* rowvox, int64_t F,
+                  const ppp_cfg* cfg, float* cons, uint32_t* cnt, int32_t impl,
+                  void* scratch, void* stream);
 
 /* ---- step 2: rank (rankPatches.cu) ----------------------------------------
  * score f32 [Z][Y][X]: border voxels -1 / -9999999, non-fg interior 0. */

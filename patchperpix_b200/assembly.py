@@ -68,25 +68,36 @@ class BlockAssembler:
         self.dp = torch.empty((F, self.P), dtype=torch.float32, device=self.dev) \
             if want_dp else None
         self.fcmask = torch.empty((F, self.W), dtype=torch.int32, device=self.dev)
+        self.rbits = None
+        if want_dp and int(self.ps[2]) <= 64:
+            self.rbits = torch.empty((F, int(self.ps[0] * self.ps[1]), 2), dtype=torch.int64,
+                                     device=self.dev)
         cc.call('ppp_prepare_patches', cc.ptr(self.pred), cc.ptr(self.flags),
                 cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.dp),
-                cc.ptr(self.fcmask), None, self.stream)
+                cc.ptr(self.fcmask), None, cc.ptr(self.rbits), self.stream)
         self._prepared = True
         return self.F
 
     # -- step 1 ------------------------------------------------------------
-    def consensus(self, want_cnt=False):
-        """create_consensus_array_cuda (consensus_array.py:71-206)."""
+    def consensus(self, want_cnt=False, impl=None):
+        """create_consensus_array_cuda (consensus_array.py:71-206).
+
+        impl 0 = tiled kernels (default), 1 = simple gather (cross-check)."""
         torch = _torch()
         if not self._prepared:
             self.prepare()
+        if impl is None:
+            impl = int(self.kwargs.get('ppp_consensus_impl', 0))
+        if self.rbits is None:
+            impl = 1
         F = max(self.F, 1)
         self.cons = torch.empty((F, self.K), dtype=torch.float32, device=self.dev)
-        self.cnt = torch.empty((F, self.K), dtype=torch.int32, device=self.dev) \
-            if want_cnt else None
-        cc.call('ppp_consensus', cc.ptr(self.dp), cc.ptr(self.flags), cc.ptr(self.fgidx),
-                cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.cons),
-                cc.ptr(self.cnt), self.stream)
+        self.cnt = torch.empty((F, self.K), dtype=torch.int32, device=self.dev)
+        scratch = torch.empty(cc.call('ppp_consensus_scratch_bytes', self.cfg),
+                              dtype=torch.uint8, device=self.dev)
+        cc.call('ppp_consensus', cc.ptr(self.dp), cc.ptr(self.rbits), cc.ptr(self.flags),
+                cc.ptr(self.fgidx), cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.cons),
+                cc.ptr(self.cnt), impl, cc.ptr(scratch), self.stream)
         return self.cons
 
     # -- step 2 ------------------------------------------------------------

@@ -68,6 +68,16 @@ __device__ __forceinline__ float fold_class(float v, float th_gt, float bg_lt)
     return 0.0f;
 }
 
+// number of rows whose voxel index is < v (fgidx of a non-row voxel stores
+// -1 - that count, see scan_write_kernel); v == V gives F.
+__device__ __forceinline__ int rows_before(const int32_t* __restrict__ fgidx, int64_t v,
+                                           int64_t V, int F)
+{
+    if (v >= V) return F;
+    int f = fgidx[v];
+    return f >= 0 ? f : -1 - f;
+}
+
 __device__ __forceinline__ double warp_sum_d(double v)
 {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

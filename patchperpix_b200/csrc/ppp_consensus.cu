@@ -84,12 +84,446 @@ consensus_naive_kernel(const float* __restrict__ dp, const uint8_t* __restrict__
     }
 }
 
-extern "C" int ppp_consensus(const float* dp, const uint8_t* flags, const int32_t* fgidx,
-                             const int32_t* rowvox, int64_t F, const ppp_cfg* cfg,
-                             float* cons, uint32_t* cnt, void* stream)
+// ---------------------------------------------------------------------------
+// vote counters from the "received" class bits (ppp_prep.cu): for the slot
+// (b, o) and every centre line (dz,dy) shared by the two windows,
+//   pos += popc(H_b & H_b'>>o),  neg += popc(H_b & L_b'>>o) + popc(L_b & H_b'>>o)
+// where the partner's word is shifted by ox so that equal bit positions mean
+// the same centre.  One thread per slot; also zero-fills `cons`, so the sum
+// kernel below only has to touch slots that can be non-zero.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+consensus_count_kernel(const unsigned long long* __restrict__ rbits,
+                       const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
+                       const int32_t* __restrict__ rowvox, ppp_cfg cfg,
+                       float* __restrict__ cons, uint32_t* __restrict__ cnt)
 {
+    Geo g = make_geo(cfg);
+    const int64_t row = blockIdx.x;
+    const int vb = rowvox[row];
+    int bz, by, bx;
+    vox_decode(g, vb, bz, by, bx);
+    const bool gated = (flags[vb] & PPP_FLAG_GATED) != 0;
+    const int nrw = g.psz * g.psy;
+    const unsigned long long* rb = rbits + row * nrw * 2;
+    for (int k = threadIdx.x; k < g.K; k += blockDim.x) {
+        uint32_t outc = 0;
+        int lin = k + g.K + 1;
+        int ox = lin % g.nx - (g.psx - 1);
+        int t = lin / g.nx;
+        int oy = t % g.ny - (g.psy - 1);
+        int oz = t / g.ny - (g.psz - 1);
+        int pz = bz + oz, py = by + oy, px = bx + ox;
+        if (gated && pz >= 0 && pz < g.Z && py >= 0 && py < g.Y && px >= 0 && px < g.X) {
+            int vp = (pz * g.Y + py) * g.X + px;
+            if (flags[vp] & PPP_FLAG_GATED) {
+                const unsigned long long* rp = rbits + (int64_t)fgidx[vp] * nrw * 2;
+                int pos = 0, neg = 0;
+                // centre offsets d (from b) with d - o inside the partner's window
+                int dz0 = max(-g.rz, oz - g.rz), dz1 = min(g.rz, oz + g.rz);
+                int dy0 = max(-g.ry, oy - g.ry), dy1 = min(g.ry, oy + g.ry);
+                for (int dz = dz0; dz <= dz1; dz++)
+                for (int dy = dy0; dy <= dy1; dy++) {
+                    int w1 = (dz + g.rz) * g.psy + (dy + g.ry);
+                    int w2 = (dz - oz + g.rz) * g.psy + (dy - oy + g.ry);
+                    unsigned long long h1 = rb[2 * w1], l1 = rb[2 * w1 + 1];
+                    unsigned long long h2 = rp[2 * w2], l2 = rp[2 * w2 + 1];
+                    if (ox >= 0) { h2 <<= ox; l2 <<= ox; } else { h2 >>= -ox; l2 >>= -ox; }
+                    pos += __popcll(h1 & h2);
+                    neg += __popcll(h1 & l2) + __popcll(l1 & h2);
+                }
+                outc = ((uint32_t)neg << 16) | (uint32_t)pos;
+            }
+        }
+        cnt[row * g.K + k] = outc;
+        // plain vote counter (no probability product): the counters are the result
+        cons[row * g.K + k] = (cfg.prod_mode == 0 && outc)
+            ? consensus_epilogue(cfg, 0.0f, (int)(outc & 0xffffu), (int)(outc >> 16)) : 0.0f;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// sums.  CTA = (base line, group of NOY consecutive offset rows (oz,oy)).
+//
+// Rows of `dp` are in raster order, so the valid centres of a line are a
+// contiguous row range (rows_before) and a centre line can be staged without
+// any index lookup.  The gated voxels of the base line and of every partner
+// line are covered greedily by T-wide x-windows ("tiles"); a work item is a
+// (base tile, partner tile) pair within reach, i.e. T*T accumulators in
+// registers.  For every centre line around the base line the patch row that
+// talks about the base line (A1) and the NOY rows that talk about the partner
+// lines (A2) are staged in shared memory, NCCH centres at a time, with
+// cp.async into a double buffer so that the copy of the next chunk overlaps
+// the arithmetic on the current one.  Every thread walks the staged centres
+// that can reach both of its tiles:
+//     acc[j][m] += D1[j] * max(D2[m],0) + max(D1[j],0) * min(D2[m],0)
+// (D = class-folded patch value; pairs that are background on both sides add
+// exact zeros: they do not vote).  Rows are padded with T zeros on both sides
+// so that a tile can be read without range checks.  Every slot has one writer
+// and a fixed summation order -> deterministic, and bit-identical to the
+// simple kernel.
+// ---------------------------------------------------------------------------
+#define CT_T 8
+#define CT_THREADS 256
+#define CT_NCCH 64
+#define CT_XMAX 2048
+#define CT_MAXTILES 512
+#define CT_MAXITEMS 6144
+#define CT_MAXLINES 128
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+
+// greedy cover of the gated voxels of one line by T-wide windows; s_out gets the
+// window start x.  Runs on one warp-0 thread after an ordered compaction.
+__device__ int ct_tiles_of_line(const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
+                                const int32_t* __restrict__ rowvox, int64_t line_base, int X,
+                                int64_t V, int F, int16_t* s_tmp, int16_t* s_out, int* s_scr)
+{
+    const int ra = rows_before(fgidx, line_base, V, F);
+    const int rb = rows_before(fgidx, line_base + X, V, F);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = CT_THREADS / 32;
+    int ntot = 0;
+    for (int base = ra; base < rb; base += CT_THREADS) {
+        int r = base + threadIdx.x;
+        int v = r < rb ? rowvox[r] : 0;
+        bool ok = r < rb && (flags[v] & PPP_FLAG_GATED);
+        unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_scr[w] = __popc(bal);
+        __syncthreads();
+        int off = ntot;
+        for (int q = 0; q < w; q++) off += s_scr[q];
+        if (ok) s_tmp[off + __popc(bal & ((1u << lane) - 1u))] = (int16_t)(v - line_base);
+        for (int q = 0; q < nw; q++) ntot += s_scr[q];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int n = 0, covered = -1;
+        for (int i = 0; i < ntot; i++) {
+            int x = s_tmp[i];
+            if (x > covered && n < CT_MAXTILES) { s_out[n++] = (int16_t)x; covered = x + CT_T - 1; }
+        }
+        s_scr[0] = n;
+    }
+    __syncthreads();
+    int n = s_scr[0];
+    __syncthreads();
+    return n;
+}
+
+template <int NOY>
+__global__ void __launch_bounds__(CT_THREADS)
+consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
+                      const int32_t* __restrict__ fgidx, const int32_t* __restrict__ rowvox,
+                      int F, ppp_cfg cfg, const uint32_t* __restrict__ cnt,
+                      float* __restrict__ cons)
+{
+    constexpr int T = CT_T;
+    Geo g = make_geo(cfg);
+    const int RS = g.psx + 2 * T;                                // padded row stride
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sA = (float*)smem_raw;                                // [2][(1+NOY)][NCCH][RS]
+    const int bufstride = (1 + NOY) * CT_NCCH * RS;
+    int32_t* s_cv = (int32_t*)(sA + 2 * bufstride);              // [2][NCCH] centre voxel index
+    int32_t* s_ra = s_cv + 2 * CT_NCCH;                          // [MAXLINES] first row per centre line
+    int32_t* s_rb = s_ra + CT_MAXLINES;                          // [MAXLINES]
+    uint32_t* s_items = (uint32_t*)(s_rb + CT_MAXLINES);         // [MAXITEMS]
+    int16_t* s_bt = (int16_t*)(s_items + CT_MAXITEMS);           // [MAXTILES] base tile starts
+    int16_t* s_pt = s_bt + CT_MAXTILES;                          // [NOY][MAXTILES]
+    int16_t* s_tmp = s_pt + NOY * CT_MAXTILES;                   // [XMAX]
+    __shared__ int s_scr[CT_THREADS / 32];
+    __shared__ int s_npt[NOY], s_nitems;
+
+    const int line = blockIdx.x;
+    const int bz = line / g.Y, by = line % g.Y;
+    const int64_t bline = (int64_t)line * g.X;
+    const int nrows_off = (g.nz * g.ny - 1) / 2 + 1;             // offset rows >= (0,0)
+    const int rlin_c = (g.nz * g.ny - 1) / 2;
+    const int tid = threadIdx.x;
+
+    // ---- tiles of the base line ----------------------------------------------
+    const int nbt = ct_tiles_of_line(flags, fgidx, rowvox, bline, g.X, g.V, F, s_tmp, s_bt, s_scr);
+    if (nbt == 0) return;
+    // ---- offset rows of this group, their partner lines and tiles --------------
+    int oz_t[NOY], oy_t[NOY];
+    int64_t pline_t[NOY];
+    bool row_ok[NOY];
+#pragma unroll
+    for (int t = 0; t < NOY; t++) {
+        int orow = blockIdx.y * NOY + t;
+        int rlin = rlin_c + orow;
+        oz_t[t] = rlin / g.ny - (g.psz - 1);
+        oy_t[t] = rlin % g.ny - (g.psy - 1);
+        int pz = bz + oz_t[t], py = by + oy_t[t];
+        row_ok[t] = orow < nrows_off && pz >= 0 && pz < g.Z && py >= 0 && py < g.Y;
+        pline_t[t] = row_ok[t] ? ((int64_t)pz * g.Y + py) * g.X : 0;
+        int np = 0;
+        if (row_ok[t])
+            np = ct_tiles_of_line(flags, fgidx, rowvox, pline_t[t], g.X, g.V, F, s_tmp,
+                                  s_pt + t * CT_MAXTILES, s_scr);
+        if (tid == 0) s_npt[t] = np;
+    }
+    __syncthreads();
+    // ---- work items, base-tile major so that a warp works on one x-neighbourhood --
+    if (tid == 0) {
+        int n = 0;
+        int lo[NOY], hi[NOY];
+        for (int t = 0; t < NOY; t++) lo[t] = hi[t] = 0;
+        for (int bt = 0; bt < nbt; bt++) {
+            const int b0 = s_bt[bt];
+            for (int t = 0; t < NOY; t++) {
+                const int np = s_npt[t];
+                const int16_t* pt = s_pt + t * CT_MAXTILES;
+                const bool same = (blockIdx.y * NOY + t) == 0;    // offset row (0,0)
+                // partner windows [p0, p0+T) with some |p - b| < psx for b in [b0, b0+T)
+                while (lo[t] < np && pt[lo[t]] + T - 1 < b0 - (g.psx - 1)) lo[t]++;
+                if (hi[t] < lo[t]) hi[t] = lo[t];
+                while (hi[t] < np && pt[hi[t]] <= b0 + T - 1 + (g.psx - 1)) hi[t]++;
+                for (int q = lo[t]; q < hi[t] && n < CT_MAXITEMS; q++) {
+                    if (same && pt[q] + T - 1 <= b0) continue;    // only p > b is stored
+                    s_items[n++] = ((uint32_t)t << 24) | ((uint32_t)bt << 12) | (uint32_t)q;
+                }
+            }
+        }
+        s_nitems = n;
+    }
+    // ---- row ranges of the centre lines around the base line -------------------
+    const int cza = max(bz - g.rz, g.rz), czb = min(bz + g.rz, g.Z - 1 - g.rz);
+    const int cya = max(by - g.ry, g.ry), cyb = min(by + g.ry, g.Y - 1 - g.ry);
+    const int ncy = cyb - cya + 1, nlines = max(czb - cza + 1, 0) * max(ncy, 0);
+    const int bxmin = s_bt[0], bxmax = s_bt[nbt - 1] + T - 1;
+    const int cxa = max(bxmin - g.rx, g.rx), cxb = min(bxmax + g.rx, g.X - 1 - g.rx);
+    for (int l = tid; l < nlines; l += CT_THREADS) {
+        int cz = cza + l / ncy, cy = cya + l % ncy;
+        int64_t cline = ((int64_t)cz * g.Y + cy) * g.X;
+        int ra = 0, rb = 0;
+        if (cxb >= cxa) {
+            ra = rows_before(fgidx, cline + cxa, g.V, F);
+            rb = rows_before(fgidx, cline + cxb + 1, g.V, F);
+        }
+        s_ra[l] = ra; s_rb[l] = rb;
+    }
+    // zero the guards of both buffers once (the data region is rewritten every stage)
+    for (int e = tid; e < 2 * bufstride; e += CT_THREADS) sA[e] = 0.0f;
+    __syncthreads();
+    const int nitems = s_nitems;
+    if (nitems == 0 || nlines <= 0) return;
+
+    for (int ibase = 0; ibase < nitems; ibase += CT_THREADS) {
+        const bool have = ibase + tid < nitems;
+        int my_t = 0, b0 = -30000, p0 = -30000;
+        if (have) {
+            uint32_t it = s_items[ibase + tid];
+            my_t = it >> 24;
+            b0 = s_bt[(it >> 12) & 0xfff];
+            p0 = s_pt[my_t * CT_MAXTILES + (it & 0xfff)];
+        }
+        // centres that can see a voxel of both windows
+        const int my_clo = max(b0, p0) - g.rx, my_chi = min(b0, p0) + T - 1 + g.rx;
+        float acc[T][T];
+#pragma unroll
+        for (int j = 0; j < T; j++)
+#pragma unroll
+            for (int m = 0; m < T; m++) acc[j][m] = 0.0f;
+
+        // ---- software pipeline over (centre line, chunk) stages -----------------
+        int st_l = 0, st_c = s_ra[0];                 // next stage to issue
+        auto skip_empty = [&]() {
+            while (st_l < nlines) {
+                bool any_act = false;
+                int cz = cza + st_l / ncy, cy = cya + st_l % ncy;
+                int q1z = bz - cz + g.rz, q1y = by - cy + g.ry;
+#pragma unroll
+                for (int t = 0; t < NOY; t++) {
+                    int q2z = q1z + oz_t[t], q2y = q1y + oy_t[t];
+                    any_act |= row_ok[t] && q2z >= 0 && q2z < g.psz && q2y >= 0 && q2y < g.psy;
+                }
+                if (any_act && st_c < s_rb[st_l]) return;
+                st_l++;
+                if (st_l < nlines) st_c = s_ra[st_l];
+            }
+        };
+        // issue the copies of stage (st_l, st_c) into buffer `buf`; returns nc
+        auto issue = [&](int buf, int& out_l) -> int {
+            skip_empty();
+            out_l = st_l;
+            if (st_l >= nlines) { cp_async_commit(); return 0; }
+            const int l = st_l, c0 = st_c;
+            const int nc = min(CT_NCCH, s_rb[l] - c0);
+            const int cz = cza + l / ncy, cy = cya + l % ncy;
+            const int q1z = bz - cz + g.rz, q1y = by - cy + g.ry;
+            const int r1 = (q1z * g.psy + q1y) * g.psx;
+            float* dst = sA + buf * bufstride;
+            for (int e = tid; e < nc * g.psx; e += CT_THREADS) {
+                int ci = e / g.psx, q = e - ci * g.psx;
+                const float* rowp = dp + (int64_t)(c0 + ci) * g.P;
+                cp_async4(dst + ci * RS + T + q, rowp + r1 + q);
+#pragma unroll
+                for (int t = 0; t < NOY; t++) {
+                    int q2z = q1z + oz_t[t], q2y = q1y + oy_t[t];
+                    if (row_ok[t] && q2z >= 0 && q2z < g.psz && q2y >= 0 && q2y < g.psy)
+                        cp_async4(dst + (1 + t) * CT_NCCH * RS + ci * RS + T + q,
+                                  rowp + (q2z * g.psy + q2y) * g.psx + q);
+                }
+            }
+            if (tid < nc) cp_async4(s_cv + buf * CT_NCCH + tid, rowvox + c0 + tid);
+            cp_async_commit();
+            st_c += nc;
+            return nc;
+        };
+
+        int cur_l, nxt_l;
+        int cur_nc = issue(0, cur_l);
+        int buf = 0;
+        while (cur_nc > 0) {
+            int nxt_nc = issue(buf ^ 1, nxt_l);
+            cp_async_wait<1>();
+            __syncthreads();
+            // ---- accumulate over the staged centres ---------------------------------
+            {
+                const int l = cur_l;
+                const int cz = cza + l / ncy, cy = cya + l % ncy;
+                const int q2z = bz - cz + g.rz + oz_t[0], q2y = by - cy + g.ry + oy_t[0];
+                (void)q2z; (void)q2y;
+                bool mine = have && my_chi >= my_clo;
+                if (mine) {
+                    int tq2z = bz - cz + g.rz, tq2y = by - cy + g.ry;
+#pragma unroll
+                    for (int t = 0; t < NOY; t++)
+                        if (my_t == t) {
+                            int a = tq2z + oz_t[t], b = tq2y + oy_t[t];
+                            mine = row_ok[t] && a >= 0 && a < g.psz && b >= 0 && b < g.psy;
+                        }
+                }
+                if (mine) {
+                    const int cbase = (int)(((int64_t)cz * g.Y + cy) * g.X);
+                    const int32_t* cv = s_cv + buf * CT_NCCH;
+                    const int nc = cur_nc;
+                    if (!(cv[0] - cbase > my_chi || cv[nc - 1] - cbase < my_clo)) {
+                        int lo = 0, hi = nc;
+                        while (lo < hi) {
+                            int mid = (lo + hi) >> 1;
+                            if (cv[mid] - cbase < my_clo) lo = mid + 1; else hi = mid;
+                        }
+                        const float* A1 = sA + buf * bufstride + T + g.rx;
+                        const float* A2 = A1 + (1 + my_t) * CT_NCCH * RS;
+                        for (int ci = lo; ci < nc; ci++) {
+                            const int cx = cv[ci] - cbase;
+                            if (cx > my_chi) break;
+                            const float* p1 = A1 + ci * RS + (b0 - cx);
+                            const float* p2 = A2 + ci * RS + (p0 - cx);
+                            // exactly one of the two products below is non-zero per pair:
+                            //   a1 * max(a2,0)          high-high (+) and background-high (-)
+                            //   max(a1,0) * min(a2,0)   high-background (-)
+                            // background-background pairs add exact zeros (they do not vote)
+                            float a1[T], h1[T], h2[T], l2[T];
+#pragma unroll
+                            for (int j = 0; j < T; j++) {
+                                a1[j] = p1[j];
+                                float a2 = p2[j];
+                                h1[j] = fmaxf(a1[j], 0.0f);
+                                h2[j] = fmaxf(a2, 0.0f);
+                                l2[j] = fminf(a2, 0.0f);
+                            }
+#pragma unroll
+                            for (int j = 0; j < T; j++)
+#pragma unroll
+                                for (int m = 0; m < T; m++)
+                                    acc[j][m] = fmaf(h1[j], l2[m], fmaf(a1[j], h2[m], acc[j][m]));
+                        }
+                    }
+                }
+            }
+            __syncthreads();                      // buffer `buf` may be overwritten now
+            buf ^= 1;
+            cur_nc = nxt_nc;
+            cur_l = nxt_l;
+        }
+        cp_async_wait<0>();
+        // ---- epilogue: normalise with the integer counters and store -----------
+        if (have) {
+            int rlin = rlin_c + blockIdx.y * NOY + my_t;
+            const int kbase = rlin * g.nx - g.K - 1 + (g.psx - 1);   // k = kbase + ox
+            const bool same = (blockIdx.y * NOY + my_t) == 0;
+            const int64_t pl = pline_t[0];
+            (void)pl;
+            int64_t pline = 0;
+#pragma unroll
+            for (int t = 0; t < NOY; t++) if (my_t == t) pline = pline_t[t];
+#pragma unroll
+            for (int j = 0; j < T; j++) {
+                const int b = b0 + j;
+                if (b >= g.X || !(flags[bline + b] & PPP_FLAG_GATED)) continue;
+                const int64_t orow = (int64_t)fgidx[bline + b] * g.K;
+#pragma unroll
+                for (int m = 0; m < T; m++) {
+                    const int p = p0 + m;
+                    const int ox = p - b;
+                    if (p >= g.X || ox <= -g.psx || ox >= g.psx) continue;
+                    if (same && ox <= 0) continue;
+                    if (!(flags[pline + p] & PPP_FLAG_GATED)) continue;
+                    const int64_t o = orow + kbase + ox;
+                    const uint32_t c = cnt[o];
+                    if (c == 0) continue;
+                    cons[o] = consensus_epilogue(cfg, acc[j][m], (int)(c & 0xffffu), (int)(c >> 16));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+#define CT_NOY 3
+
+static size_t rows_smem(const Geo& g)
+{
+    int RS = g.psx + 2 * CT_T;
+    return (size_t)2 * (1 + CT_NOY) * CT_NCCH * RS * 4 + 2 * CT_NCCH * 4 + 2 * CT_MAXLINES * 4 +
+           (size_t)CT_MAXITEMS * 4 + (size_t)(1 + CT_NOY) * CT_MAXTILES * 2 + CT_XMAX * 2;
+}
+
+extern "C" int64_t ppp_consensus_scratch_bytes(const ppp_cfg* cfg)
+{
+    (void)cfg;
+    return 256;
+}
+
+extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8_t* flags,
+                             const int32_t* fgidx, const int32_t* rowvox, int64_t F,
+                             const ppp_cfg* cfg, float* cons, uint32_t* cnt, int32_t impl,
+                             void* scratch, void* stream)
+{
+    (void)scratch;
     if (F <= 0) return 0;
-    consensus_naive_kernel<<<(unsigned)F, 128, 0, (cudaStream_t)stream>>>(
-        dp, flags, fgidx, rowvox, *cfg, cons, cnt);
-    return ppp_check("ppp_consensus");
+    cudaStream_t s = (cudaStream_t)stream;
+    Geo g = make_geo(*cfg);
+    if (impl == 1) {
+        consensus_naive_kernel<<<(unsigned)F, 128, 0, s>>>(dp, flags, fgidx, rowvox, *cfg,
+                                                           cons, cnt);
+        return ppp_check("ppp_consensus(naive)");
+    }
+    if (rbits == nullptr || cnt == nullptr)
+        return ppp_fail(-1, "ppp_consensus: tiled path needs rbits and cnt");
+    if (g.psx > 64) return ppp_fail(-1, "ppp_consensus: psx > 64 unsupported by the bit path");
+    if (g.X > CT_XMAX) return ppp_fail(-1, "ppp_consensus: X > 2048 unsupported, use blocks");
+    if (g.psz * g.psy > CT_MAXLINES)
+        return ppp_fail(-1, "ppp_consensus: more than 128 centre lines per window");
+    consensus_count_kernel<<<(unsigned)F, 256, 0, s>>>(
+        (const unsigned long long*)rbits, flags, fgidx, rowvox, *cfg, cons, cnt);
+    if (cfg->prod_mode == 0) return ppp_check("ppp_consensus(count)");   // no float sums needed
+    size_t smem = rows_smem(g);
+    cudaError_t e = cudaFuncSetAttribute(consensus_rows_kernel<CT_NOY>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return ppp_fail((int)e, "ppp_consensus: smem attribute");
+    int nrows_off = (g.nz * g.ny - 1) / 2 + 1;
+    dim3 grid((unsigned)(g.Z * g.Y), (unsigned)((nrows_off + CT_NOY - 1) / CT_NOY));
+    consensus_rows_kernel<CT_NOY><<<grid, CT_THREADS, smem, s>>>(
+        dp, flags, fgidx, rowvox, (int)F, *cfg, cnt, cons);
+    return ppp_check("ppp_consensus(rows)");
 }

@@ -141,7 +141,7 @@ __global__ void scan_write_kernel(const uint8_t* __restrict__ flags, int64_t V,
         int64_t v = base + i;
         if (v < V) {
             if (f[i]) { fgidx[v] = row; rowvox[row] = (int32_t)v; row++; }
-            else fgidx[v] = -1;
+            else fgidx[v] = -1 - row;     // encodes the number of rows before v
         }
     }
 }
@@ -228,16 +228,65 @@ prepare_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags
     }
 }
 
+// ---------------------------------------------------------------------------
+// "received" class bits: for every gated voxel b and every centre line offset
+// (dz,dy), one 64-bit word whose bit (dx + rx) says that the centre c = b + d
+// calls b "high" (H word) or "background" (L word).  The vote COUNTERS of the
+// consensus are popcounts over these words (ppp_consensus.cu).  Lanes walk
+// consecutive rows, so the dense plane reads are coalesced.
+// rbits u64 [F][psz*psy][2].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+received_bits_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags,
+                     const int32_t* __restrict__ rowvox, int64_t F, ppp_cfg cfg,
+                     unsigned long long* __restrict__ rbits)
+{
+    Geo g = make_geo(cfg);
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= F) return;
+    const int w = blockIdx.y;                   // (dz + rz) * psy + (dy + ry)
+    const int dz = w / g.psy - g.rz, dy = w % g.psy - g.ry;
+    const int v = rowvox[row];
+    unsigned long long hb = 0ull, lb = 0ull;
+    if (flags[v] & PPP_FLAG_GATED) {
+        int bz, by, bx;
+        vox_decode(g, v, bz, by, bx);
+        const int cz = bz + dz, cy = by + dy;
+        if (cz >= g.rz && cz < g.Z - g.rz && cy >= g.ry && cy < g.Y - g.ry) {
+            const int64_t line = ((int64_t)cz * g.Y + cy) * g.X;
+            const int porow = ((g.rz - dz) * g.psy + (g.ry - dy)) * g.psx;
+            for (int t = 0; t < g.psx; t++) {
+                int cx = bx - g.rx + t;
+                if (cx < g.rx || cx >= g.X - g.rx) continue;
+                if (!(flags[line + cx] & PPP_FLAG_CENTRE)) continue;
+                // pixel b seen from centre c sits at patch index r - d
+                float val = pred[(int64_t)(porow + (g.psx - 1 - t)) * g.V + line + cx];
+                if (val > cfg.th_gt) hb |= 1ull << t;
+                else if (val < cfg.bg_lt) lb |= 1ull << t;
+            }
+        }
+    }
+    const int64_t o = (row * (g.psz * g.psy) + w) * 2;
+    rbits[o] = hb;
+    rbits[o + 1] = lb;
+}
+
 extern "C" int ppp_prepare_patches(const float* pred, const uint8_t* flags,
                                    const int32_t* rowvox, int64_t F,
                                    const ppp_cfg* cfg, float* dp,
                                    uint32_t* fcmask, uint32_t* ptmask,
-                                   void* stream)
+                                   uint64_t* rbits, void* stream)
 {
     if (F <= 0) return 0;
     Geo g = make_geo(*cfg);
     dim3 grid((unsigned)((F + 31) / 32), (unsigned)g.W);
     prepare_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         pred, flags, rowvox, F, *cfg, dp, fcmask, ptmask);
+    if (rbits != nullptr) {
+        if (g.psx > 64) return ppp_fail(-1, "ppp_prepare_patches: psx > 64 has no bit path");
+        dim3 grid2((unsigned)((F + 127) / 128), (unsigned)(g.psz * g.psy));
+        received_bits_kernel<<<grid2, 128, 0, (cudaStream_t)stream>>>(
+            pred, flags, rowvox, F, *cfg, (unsigned long long*)rbits);
+    }
     return ppp_check("ppp_prepare_patches");
 }

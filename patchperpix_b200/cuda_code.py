@@ -80,6 +80,8 @@ def make_cfg(shape, patchshape, **kwargs):
     c = PppCfg()
     c.Z, c.Y, c.X = (int(s) for s in shape)
     c.psz, c.psy, c.psx = (int(p) for p in patchshape)
+    assert c.psz % 2 == 1 and c.psy % 2 == 1 and c.psx % 2 == 1, \
+        "patchshape must be odd (the centre channel is P // 2)"
     c.th_gt = _f32_floor(th)
     c.bg_lt = _f32_ceil(bg)
     c.fc_gt = float(np.float32(kwargs.get('fc_threshold', 0.5)))
@@ -102,8 +104,9 @@ _SIGS = {
     'ppp_gate': (ctypes.c_int, ['p', 'p', 'p', 'cfg', 'p', 'p']),
     'ppp_compact_scratch_bytes': (ctypes.c_int64, ['i64']),
     'ppp_compact': (ctypes.c_int, ['p', 'i64', 'p', 'p', 'p', 'p', 'p']),
-    'ppp_prepare_patches': (ctypes.c_int, ['p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p', 'p']),
-    'ppp_consensus': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
+    'ppp_prepare_patches': (ctypes.c_int, ['p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p', 'p', 'p']),
+    'ppp_consensus_scratch_bytes': (ctypes.c_int64, ['cfg']),
+    'ppp_consensus': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'i32', 'p', 'p']),
     'ppp_rank': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
     'ppp_rank_sort_scratch_bytes': (ctypes.c_int64, ['i64']),
     'ppp_rank_sort': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'p', 'p']),

@@ -118,3 +118,17 @@ def test_end_to_end_labels_identical(name):
     pairs, aff = vi.to_instance_seg(pred.copy(), fg.copy(), fg.copy(), g['numinst'].copy(),
                                     ps.copy(), **dict(kw, return_intermediates=True))
     assert np.array_equal(pairs, g['pairs'])
+
+
+@pytest.mark.parametrize('name', gu.NAMES)
+def test_tiled_and_simple_consensus_agree(name):
+    """the two CUDA implementations of step 1: counters identical, sums close."""
+    g, kw, ps, pred, fg, asm = _asm(name)
+    asm.prepare()
+    asm.consensus(impl=0)
+    c0, n0 = asm.cons.clone(), asm.cnt.clone()
+    asm.consensus(impl=1)
+    import torch
+    assert torch.equal(n0, asm.cnt)
+    scale = 1.0 if kw.get('consensus_norm_aff', True) else float(np.prod(ps))
+    assert float((c0 - asm.cons).abs().max()) <= CONS_TOL * scale
