@@ -65,8 +65,10 @@ class BlockAssembler:
         self.F = int(nrows.item())          # the one host sync: sizes the outputs
         self.rowvox = self.rowvox[:self.F]
         F = max(self.F, 1)
-        self.dp = torch.empty((F, self.P), dtype=torch.float32, device=self.dev) \
-            if want_dp else None
+        # padded layout [F][psz*psy][rsg] with zero guards (csrc/ppp_common.cuh)
+        rsg = ((int(self.ps[2]) + 16 + 3) // 4) * 4
+        self.dp = torch.zeros((F, int(self.ps[0] * self.ps[1]) * rsg), dtype=torch.float32,
+                              device=self.dev) if want_dp else None
         self.fcmask = torch.empty((F, self.W), dtype=torch.int32, device=self.dev)
         self.rbits = None
         if want_dp and int(self.ps[2]) <= 64:

@@ -13,7 +13,15 @@ struct Geo {
     int K;                 // (nz*ny*nx-1)/2
     int64_t V;
     int W;                 // (P+31)/32
+    int rsg;               // padded length of one patch x-row in `dp` (guards + psx, x4)
+    int rp;                // floats per `dp` row: psz*psy*rsg
 };
+
+// `dp` layout: [row][patch row (qz,qy)][rsg]; the psx values of a patch x-row
+// sit at [DP_GUARD, DP_GUARD+psx), the guards are zero so that a T-wide tile can
+// be read without range checks; slot 0 of every patch row holds the x coordinate
+// of the centre (int bits).  Rows are 16-byte aligned: TMA boxes map onto them.
+#define DP_GUARD 8
 
 __host__ __device__ inline Geo make_geo(const ppp_cfg& c)
 {
@@ -26,6 +34,8 @@ __host__ __device__ inline Geo make_geo(const ppp_cfg& c)
     g.K = (g.nz * g.ny * g.nx - 1) / 2;
     g.V = (int64_t)c.Z * c.Y * c.X;
     g.W = (g.P + 31) / 32;
+    g.rsg = ((c.psx + 2 * DP_GUARD + 3) / 4) * 4;
+    g.rp = c.psz * c.psy * g.rsg;
     return g;
 }
 
@@ -43,6 +53,12 @@ __device__ __forceinline__ void po_decode(const Geo& g, int po, int& qz, int& qy
     int t = po / g.psx;
     qy = t % g.psy;
     qz = t / g.psy;
+}
+
+// offset of patch channel po inside a `dp` row
+__host__ __device__ __forceinline__ int dp_off(const Geo& g, int po)
+{
+    return (po / g.psx) * g.rsg + DP_GUARD + po % g.psx;
 }
 
 // position of patch pixel po in the (2ps-1)^3 offset raster: k(o) for

@@ -12,6 +12,7 @@
 //            minus the both-background products    include/ppp_b200.h)
 // so the counters are integers, the float sum has a fixed order (deterministic,
 // unlike the reference's atomics) and normalisation is fused into the epilogue.
+#include <cuda.h>
 #include "ppp_common.cuh"
 #include "ppp_api.cuh"
 
@@ -68,8 +69,8 @@ consensus_naive_kernel(const float* __restrict__ dp, const uint8_t* __restrict__
                     if (rc < 0) continue;       // not fg => not a centre (interior by the clamps)
                     int po1 = ((bz - cz + g.rz) * g.psy + (by - cy + g.ry)) * g.psx + (bx - cx + g.rx);
                     int po2 = ((pz - cz + g.rz) * g.psy + (py - cy + g.ry)) * g.psx + (px - cx + g.rx);
-                    float d1 = dp[(int64_t)rc * g.P + po1];
-                    float d2 = dp[(int64_t)rc * g.P + po2];
+                    float d1 = dp[(int64_t)rc * g.rp + dp_off(g, po1)];
+                    float d2 = dp[(int64_t)rc * g.rp + dp_off(g, po2)];
                     bool h1 = d1 > 0.0f, h2 = d2 > 0.0f, l1 = d1 < 0.0f, l2 = d2 < 0.0f;
                     pos += (h1 && h2);
                     neg += (h1 && l2) || (l1 && h2);
@@ -146,22 +147,23 @@ consensus_count_kernel(const unsigned long long* __restrict__ rbits,
 // sums.  CTA = (base line, group of NOY consecutive offset rows (oz,oy)).
 //
 // Rows of `dp` are in raster order, so the valid centres of a line are a
-// contiguous row range (rows_before) and a centre line can be staged without
-// any index lookup.  The gated voxels of the base line and of every partner
-// line are covered greedily by T-wide x-windows ("tiles"); a work item is a
-// (base tile, partner tile) pair within reach, i.e. T*T accumulators in
-// registers.  For every centre line around the base line the patch row that
-// talks about the base line (A1) and the NOY rows that talk about the partner
-// lines (A2) are staged in shared memory, NCCH centres at a time, with
-// cp.async into a double buffer so that the copy of the next chunk overlaps
-// the arithmetic on the current one.  Every thread walks the staged centres
-// that can reach both of its tiles:
+// contiguous row range (rows_before) and one patch x-row of NCCH consecutive
+// centres is a rectangular box of the 3-D tensor dp[row][patch row][rsg]:
+// it is fetched by ONE TMA instruction (cp.async.bulk.tensor.3d) that signals
+// an mbarrier, into a double buffer, so the copy of the next chunk overlaps
+// the arithmetic on the current one and costs no LSU issue slots.
+// The gated voxels of the base line and of every partner line are covered
+// greedily by T-wide x-windows ("tiles"); a work item is a (base tile, partner
+// tile) pair within reach, i.e. T*T accumulators in registers.  For every
+// centre line around the base line the patch row that talks about the base
+// line (A1) and the NOY rows that talk about the partner lines (A2) are
+// staged, and every thread walks the staged centres that can reach both of
+// its tiles:
 //     acc[j][m] += D1[j] * max(D2[m],0) + max(D1[j],0) * min(D2[m],0)
 // (D = class-folded patch value; pairs that are background on both sides add
-// exact zeros: they do not vote).  Rows are padded with T zeros on both sides
-// so that a tile can be read without range checks.  Every slot has one writer
-// and a fixed summation order -> deterministic, and bit-identical to the
-// simple kernel.
+// exact zeros: they do not vote).  The zero guards of the dp layout let a tile
+// be read without range checks.  Every slot has one writer and a fixed
+// summation order -> deterministic, and bit-identical to the simple kernel.
 // ---------------------------------------------------------------------------
 #define CT_T 8
 #define CT_THREADS 256
@@ -171,17 +173,44 @@ consensus_count_kernel(const unsigned long long* __restrict__ rbits,
 #define CT_MAXITEMS 6144
 #define CT_MAXLINES 128
 
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(a), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" :: "r"(a), "r"(parity) : "memory");
+}
+// one box {rsg, 1, NCCH} of dp -> shared memory, completion on `bar`
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* tmap, uint64_t* bar,
+                                            int c0, int c1, int c2)
 {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(sa), "l"(gmem));
+    unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];\n"
+        :: "r"(sa), "l"((uint64_t)tmap), "r"(ba), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
 
 // greedy cover of the gated voxels of one line by T-wide windows; s_out gets the
-// window start x.  Runs on one warp-0 thread after an ordered compaction.
+// window start x.
 __device__ int ct_tiles_of_line(const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
                                 const int32_t* __restrict__ rowvox, int64_t line_base, int X,
                                 int64_t V, int F, int16_t* s_tmp, int16_t* s_out, int* s_scr)
@@ -219,19 +248,19 @@ __device__ int ct_tiles_of_line(const uint8_t* __restrict__ flags, const int32_t
 
 template <int NOY>
 __global__ void __launch_bounds__(CT_THREADS)
-consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
+consensus_rows_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ flags,
                       const int32_t* __restrict__ fgidx, const int32_t* __restrict__ rowvox,
                       int F, ppp_cfg cfg, const uint32_t* __restrict__ cnt,
                       float* __restrict__ cons)
 {
     constexpr int T = CT_T;
     Geo g = make_geo(cfg);
-    const int RS = g.psx + 2 * T;                                // padded row stride
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int RS = g.rsg;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sA = (float*)smem_raw;                                // [2][(1+NOY)][NCCH][RS]
-    const int bufstride = (1 + NOY) * CT_NCCH * RS;
-    int32_t* s_cv = (int32_t*)(sA + 2 * bufstride);              // [2][NCCH] centre voxel index
-    int32_t* s_ra = s_cv + 2 * CT_NCCH;                          // [MAXLINES] first row per centre line
+    const int substride = CT_NCCH * RS;                          // one staged patch row
+    const int bufstride = (1 + NOY) * substride;
+    int32_t* s_ra = (int32_t*)(sA + 2 * bufstride);              // [MAXLINES] first row per centre line
     int32_t* s_rb = s_ra + CT_MAXLINES;                          // [MAXLINES]
     uint32_t* s_items = (uint32_t*)(s_rb + CT_MAXLINES);         // [MAXITEMS]
     int16_t* s_bt = (int16_t*)(s_items + CT_MAXITEMS);           // [MAXTILES] base tile starts
@@ -239,6 +268,7 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
     int16_t* s_tmp = s_pt + NOY * CT_MAXTILES;                   // [XMAX]
     __shared__ int s_scr[CT_THREADS / 32];
     __shared__ int s_npt[NOY], s_nitems;
+    __shared__ __align__(8) uint64_t s_full[2];
 
     const int line = blockIdx.x;
     const int bz = line / g.Y, by = line % g.Y;
@@ -292,6 +322,9 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
             }
         }
         s_nitems = n;
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     // ---- row ranges of the centre lines around the base line -------------------
     const int cza = max(bz - g.rz, g.rz), czb = min(bz + g.rz, g.Z - 1 - g.rz);
@@ -309,11 +342,10 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
         }
         s_ra[l] = ra; s_rb[l] = rb;
     }
-    // zero the guards of both buffers once (the data region is rewritten every stage)
-    for (int e = tid; e < 2 * bufstride; e += CT_THREADS) sA[e] = 0.0f;
     __syncthreads();
     const int nitems = s_nitems;
     if (nitems == 0 || nlines <= 0) return;
+    unsigned phase0 = 0, phase1 = 0;
 
     for (int ibase = 0; ibase < nitems; ibase += CT_THREADS) {
         const bool have = ibase + tid < nitems;
@@ -334,46 +366,41 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
 
         // ---- software pipeline over (centre line, chunk) stages -----------------
         int st_l = 0, st_c = s_ra[0];                 // next stage to issue
-        auto skip_empty = [&]() {
-            while (st_l < nlines) {
-                bool any_act = false;
-                int cz = cza + st_l / ncy, cy = cya + st_l % ncy;
-                int q1z = bz - cz + g.rz, q1y = by - cy + g.ry;
+        // offset rows that have a patch row in centre line l (bit t), 0 = none
+        auto act_mask = [&](int l) -> unsigned {
+            int cz = cza + l / ncy, cy = cya + l % ncy;
+            int q1z = bz - cz + g.rz, q1y = by - cy + g.ry;
+            unsigned m = 0;
 #pragma unroll
-                for (int t = 0; t < NOY; t++) {
-                    int q2z = q1z + oz_t[t], q2y = q1y + oy_t[t];
-                    any_act |= row_ok[t] && q2z >= 0 && q2z < g.psz && q2y >= 0 && q2y < g.psy;
-                }
-                if (any_act && st_c < s_rb[st_l]) return;
+            for (int t = 0; t < NOY; t++) {
+                int q2z = q1z + oz_t[t], q2y = q1y + oy_t[t];
+                if (row_ok[t] && q2z >= 0 && q2z < g.psz && q2y >= 0 && q2y < g.psy) m |= 1u << t;
+            }
+            return m;
+        };
+        // issue the TMA copies of the next non-empty stage into buffer `buf`
+        auto issue = [&](int buf, int& out_l) -> int {
+            while (st_l < nlines && !(act_mask(st_l) && st_c < s_rb[st_l])) {
                 st_l++;
                 if (st_l < nlines) st_c = s_ra[st_l];
             }
-        };
-        // issue the copies of stage (st_l, st_c) into buffer `buf`; returns nc
-        auto issue = [&](int buf, int& out_l) -> int {
-            skip_empty();
             out_l = st_l;
-            if (st_l >= nlines) { cp_async_commit(); return 0; }
+            if (st_l >= nlines) return 0;
             const int l = st_l, c0 = st_c;
             const int nc = min(CT_NCCH, s_rb[l] - c0);
-            const int cz = cza + l / ncy, cy = cya + l % ncy;
-            const int q1z = bz - cz + g.rz, q1y = by - cy + g.ry;
-            const int r1 = (q1z * g.psy + q1y) * g.psx;
-            float* dst = sA + buf * bufstride;
-            for (int e = tid; e < nc * g.psx; e += CT_THREADS) {
-                int ci = e / g.psx, q = e - ci * g.psx;
-                const float* rowp = dp + (int64_t)(c0 + ci) * g.P;
-                cp_async4(dst + ci * RS + T + q, rowp + r1 + q);
+            if (tid == 0) {
+                const unsigned am = act_mask(l);
+                const int cz = cza + l / ncy, cy = cya + l % ncy;
+                const int q1z = bz - cz + g.rz, q1y = by - cy + g.ry;
+                float* dst = sA + buf * bufstride;
+                mbar_expect_tx(&s_full[buf], (unsigned)((1 + __popc(am)) * substride * 4));
+                tma_load_3d(dst, &tmap, &s_full[buf], 0, q1z * g.psy + q1y, c0);
 #pragma unroll
-                for (int t = 0; t < NOY; t++) {
-                    int q2z = q1z + oz_t[t], q2y = q1y + oy_t[t];
-                    if (row_ok[t] && q2z >= 0 && q2z < g.psz && q2y >= 0 && q2y < g.psy)
-                        cp_async4(dst + (1 + t) * CT_NCCH * RS + ci * RS + T + q,
-                                  rowp + (q2z * g.psy + q2y) * g.psx + q);
-                }
+                for (int t = 0; t < NOY; t++)
+                    if (am & (1u << t))
+                        tma_load_3d(dst + (1 + t) * substride, &tmap, &s_full[buf], 0,
+                                    (q1z + oz_t[t]) * g.psy + (q1y + oy_t[t]), c0);
             }
-            if (tid < nc) cp_async4(s_cv + buf * CT_NCCH + tid, rowvox + c0 + tid);
-            cp_async_commit();
             st_c += nc;
             return nc;
         };
@@ -383,60 +410,45 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
         int buf = 0;
         while (cur_nc > 0) {
             int nxt_nc = issue(buf ^ 1, nxt_l);
-            cp_async_wait<1>();
-            __syncthreads();
+            if (buf == 0) { mbar_wait(&s_full[0], phase0); phase0 ^= 1; }
+            else { mbar_wait(&s_full[1], phase1); phase1 ^= 1; }
             // ---- accumulate over the staged centres ---------------------------------
-            {
-                const int l = cur_l;
-                const int cz = cza + l / ncy, cy = cya + l % ncy;
-                const int q2z = bz - cz + g.rz + oz_t[0], q2y = by - cy + g.ry + oy_t[0];
-                (void)q2z; (void)q2y;
-                bool mine = have && my_chi >= my_clo;
-                if (mine) {
-                    int tq2z = bz - cz + g.rz, tq2y = by - cy + g.ry;
+            bool mine = have && my_chi >= my_clo && ((act_mask(cur_l) >> my_t) & 1u);
+            if (mine) {
+                const float* A1 = sA + buf * bufstride;
+                const int nc = cur_nc;
+                const int cx_first = __float_as_int(A1[0]);
+                const int cx_last = __float_as_int(A1[(nc - 1) * RS]);
+                if (!(cx_first > my_chi || cx_last < my_clo)) {
+                    int lo = 0, hi = nc;
+                    while (lo < hi) {
+                        int mid = (lo + hi) >> 1;
+                        if (__float_as_int(A1[mid * RS]) < my_clo) lo = mid + 1; else hi = mid;
+                    }
+                    const float* A2 = A1 + (1 + my_t) * substride;
+                    for (int ci = lo; ci < nc; ci++) {
+                        const int cx = __float_as_int(A1[ci * RS]);
+                        if (cx > my_chi) break;
+                        const float* p1 = A1 + ci * RS + DP_GUARD + g.rx + (b0 - cx);
+                        const float* p2 = A2 + ci * RS + DP_GUARD + g.rx + (p0 - cx);
+                        // exactly one of the two products below is non-zero per pair:
+                        //   a1 * max(a2,0)          high-high (+) and background-high (-)
+                        //   max(a1,0) * min(a2,0)   high-background (-)
+                        // background-background pairs add exact zeros (they do not vote)
+                        float a1[T], h1[T], h2[T], l2[T];
 #pragma unroll
-                    for (int t = 0; t < NOY; t++)
-                        if (my_t == t) {
-                            int a = tq2z + oz_t[t], b = tq2y + oy_t[t];
-                            mine = row_ok[t] && a >= 0 && a < g.psz && b >= 0 && b < g.psy;
+                        for (int j = 0; j < T; j++) {
+                            a1[j] = p1[j];
+                            float a2 = p2[j];
+                            h1[j] = fmaxf(a1[j], 0.0f);
+                            h2[j] = fmaxf(a2, 0.0f);
+                            l2[j] = fminf(a2, 0.0f);
                         }
-                }
-                if (mine) {
-                    const int cbase = (int)(((int64_t)cz * g.Y + cy) * g.X);
-                    const int32_t* cv = s_cv + buf * CT_NCCH;
-                    const int nc = cur_nc;
-                    if (!(cv[0] - cbase > my_chi || cv[nc - 1] - cbase < my_clo)) {
-                        int lo = 0, hi = nc;
-                        while (lo < hi) {
-                            int mid = (lo + hi) >> 1;
-                            if (cv[mid] - cbase < my_clo) lo = mid + 1; else hi = mid;
-                        }
-                        const float* A1 = sA + buf * bufstride + T + g.rx;
-                        const float* A2 = A1 + (1 + my_t) * CT_NCCH * RS;
-                        for (int ci = lo; ci < nc; ci++) {
-                            const int cx = cv[ci] - cbase;
-                            if (cx > my_chi) break;
-                            const float* p1 = A1 + ci * RS + (b0 - cx);
-                            const float* p2 = A2 + ci * RS + (p0 - cx);
-                            // exactly one of the two products below is non-zero per pair:
-                            //   a1 * max(a2,0)          high-high (+) and background-high (-)
-                            //   max(a1,0) * min(a2,0)   high-background (-)
-                            // background-background pairs add exact zeros (they do not vote)
-                            float a1[T], h1[T], h2[T], l2[T];
 #pragma unroll
-                            for (int j = 0; j < T; j++) {
-                                a1[j] = p1[j];
-                                float a2 = p2[j];
-                                h1[j] = fmaxf(a1[j], 0.0f);
-                                h2[j] = fmaxf(a2, 0.0f);
-                                l2[j] = fminf(a2, 0.0f);
-                            }
+                        for (int j = 0; j < T; j++)
 #pragma unroll
-                            for (int j = 0; j < T; j++)
-#pragma unroll
-                                for (int m = 0; m < T; m++)
-                                    acc[j][m] = fmaf(h1[j], l2[m], fmaf(a1[j], h2[m], acc[j][m]));
-                        }
+                            for (int m = 0; m < T; m++)
+                                acc[j][m] = fmaf(h1[j], l2[m], fmaf(a1[j], h2[m], acc[j][m]));
                     }
                 }
             }
@@ -445,14 +457,11 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
             cur_nc = nxt_nc;
             cur_l = nxt_l;
         }
-        cp_async_wait<0>();
         // ---- epilogue: normalise with the integer counters and store -----------
         if (have) {
             int rlin = rlin_c + blockIdx.y * NOY + my_t;
             const int kbase = rlin * g.nx - g.K - 1 + (g.psx - 1);   // k = kbase + ox
             const bool same = (blockIdx.y * NOY + my_t) == 0;
-            const int64_t pl = pline_t[0];
-            (void)pl;
             int64_t pline = 0;
 #pragma unroll
             for (int t = 0; t < NOY; t++) if (my_t == t) pline = pline_t[t];
@@ -483,9 +492,35 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
 
 static size_t rows_smem(const Geo& g)
 {
-    int RS = g.psx + 2 * CT_T;
-    return (size_t)2 * (1 + CT_NOY) * CT_NCCH * RS * 4 + 2 * CT_NCCH * 4 + 2 * CT_MAXLINES * 4 +
-           (size_t)CT_MAXITEMS * 4 + (size_t)(1 + CT_NOY) * CT_MAXTILES * 2 + CT_XMAX * 2;
+    return (size_t)2 * (1 + CT_NOY) * CT_NCCH * g.rsg * 4 + 2 * CT_MAXLINES * 4 +
+           (size_t)CT_MAXITEMS * 4 + (size_t)(1 + CT_NOY) * CT_MAXTILES * 2 + CT_XMAX * 2 + 128;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_dp_tensor_map(CUtensorMap* tm, const float* dp, int64_t F, const Geo& g)
+{
+    static PFN_encodeTiled enc = nullptr;
+    if (enc == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || fn == nullptr)
+            return ppp_fail(-1, "ppp_consensus: cuTensorMapEncodeTiled unavailable");
+        enc = (PFN_encodeTiled)fn;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)g.rsg, (cuuint64_t)(g.psz * g.psy), (cuuint64_t)F};
+    cuuint64_t strides[2] = {(cuuint64_t)g.rsg * 4, (cuuint64_t)g.rp * 4};
+    cuuint32_t box[3] = {(cuuint32_t)g.rsg, 1u, (cuuint32_t)CT_NCCH};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)dp, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ppp_fail(-1, "ppp_consensus: cuTensorMapEncodeTiled failed");
+    return 0;
 }
 
 extern "C" int64_t ppp_consensus_scratch_bytes(const ppp_cfg* cfg)
@@ -517,6 +552,9 @@ extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8
     consensus_count_kernel<<<(unsigned)F, 256, 0, s>>>(
         (const unsigned long long*)rbits, flags, fgidx, rowvox, *cfg, cons, cnt);
     if (cfg->prod_mode == 0) return ppp_check("ppp_consensus(count)");   // no float sums needed
+    CUtensorMap tm;
+    int rc = make_dp_tensor_map(&tm, dp, F, g);
+    if (rc) return rc;
     size_t smem = rows_smem(g);
     cudaError_t e = cudaFuncSetAttribute(consensus_rows_kernel<CT_NOY>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -524,6 +562,6 @@ extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8
     int nrows_off = (g.nz * g.ny - 1) / 2 + 1;
     dim3 grid((unsigned)(g.Z * g.Y), (unsigned)((nrows_off + CT_NOY - 1) / CT_NOY));
     consensus_rows_kernel<CT_NOY><<<grid, CT_THREADS, smem, s>>>(
-        dp, flags, fgidx, rowvox, (int)F, *cfg, cnt, cons);
+        tm, flags, fgidx, rowvox, (int)F, *cfg, cnt, cons);
     return ppp_check("ppp_consensus(rows)");
 }

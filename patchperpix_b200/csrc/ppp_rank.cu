@@ -62,7 +62,7 @@ rank_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
         int qz = 0, qy = 0, qx = 0, pv = 0;
         bool gated = false;
         if (po < g.P) {
-            d = dp[row * g.P + po];
+            d = dp[row * g.rp + dp_off(g, po)];
             po_decode(g, po, qz, qy, qx);
             pv = ((cz + qz - g.rz) * g.Y + (cy + qy - g.ry)) * g.X + (cx + qx - g.rx);
             gated = (flags[pv] & PPP_FLAG_GATED) != 0;
