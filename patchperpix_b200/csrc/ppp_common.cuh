@@ -17,10 +17,12 @@ struct Geo {
     int rp;                // floats per `dp` row: psz*psy*rsg
 };
 
-// `dp` layout: [row][patch row (qz,qy)][rsg]; the psx values of a patch x-row
-// sit at [DP_GUARD, DP_GUARD+psx), the guards are zero so that a T-wide tile can
-// be read without range checks; slot 0 of every patch row holds the x coordinate
-// of the centre (int bits).  Rows are 16-byte aligned: TMA boxes map onto them.
+// `dp` layout: [patch row (qz,qy)][row][rsg] — patch-row major, so that one
+// patch x-row of CONSECUTIVE centres is one contiguous, 16-byte aligned block
+// that a single bulk copy (cp.async.bulk, TMA engine) brings into shared memory.
+// The psx values of a patch x-row sit at [DP_GUARD, DP_GUARD+psx), the guards
+// are zero so that a T-wide tile can be read without range checks; slot 0 of
+// every patch row holds the x coordinate of the centre (int bits).
 #define DP_GUARD 8
 
 __host__ __device__ inline Geo make_geo(const ppp_cfg& c)
@@ -55,10 +57,10 @@ __device__ __forceinline__ void po_decode(const Geo& g, int po, int& qz, int& qy
     qz = t / g.psy;
 }
 
-// offset of patch channel po inside a `dp` row
-__host__ __device__ __forceinline__ int dp_off(const Geo& g, int po)
+// index of patch channel po of row `row` in `dp` (F rows in total)
+__host__ __device__ __forceinline__ int64_t dp_index(const Geo& g, int64_t F, int64_t row, int po)
 {
-    return (po / g.psx) * g.rsg + DP_GUARD + po % g.psx;
+    return ((int64_t)(po / g.psx) * F + row) * g.rsg + DP_GUARD + po % g.psx;
 }
 
 // position of patch pixel po in the (2ps-1)^3 offset raster: k(o) for

@@ -36,7 +36,8 @@ __device__ __forceinline__ float consensus_epilogue(const ppp_cfg& cfg, float su
 __global__ void __launch_bounds__(128)
 consensus_naive_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
                        const int32_t* __restrict__ fgidx, const int32_t* __restrict__ rowvox,
-                       ppp_cfg cfg, float* __restrict__ cons, uint32_t* __restrict__ cnt)
+                       int64_t F, ppp_cfg cfg, float* __restrict__ cons,
+                       uint32_t* __restrict__ cnt)
 {
     Geo g = make_geo(cfg);
     const int64_t row = blockIdx.x;
@@ -69,8 +70,8 @@ consensus_naive_kernel(const float* __restrict__ dp, const uint8_t* __restrict__
                     if (rc < 0) continue;       // not fg => not a centre (interior by the clamps)
                     int po1 = ((bz - cz + g.rz) * g.psy + (by - cy + g.ry)) * g.psx + (bx - cx + g.rx);
                     int po2 = ((pz - cz + g.rz) * g.psy + (py - cy + g.ry)) * g.psx + (px - cx + g.rx);
-                    float d1 = dp[(int64_t)rc * g.rp + dp_off(g, po1)];
-                    float d2 = dp[(int64_t)rc * g.rp + dp_off(g, po2)];
+                    float d1 = dp[dp_index(g, F, rc, po1)];
+                    float d2 = dp[dp_index(g, F, rc, po2)];
                     bool h1 = d1 > 0.0f, h2 = d2 > 0.0f, l1 = d1 < 0.0f, l2 = d2 < 0.0f;
                     pos += (h1 && h2);
                     neg += (h1 && l2) || (l1 && h2);
@@ -147,11 +148,11 @@ consensus_count_kernel(const unsigned long long* __restrict__ rbits,
 // sums.  CTA = (base line, group of NOY consecutive offset rows (oz,oy)).
 //
 // Rows of `dp` are in raster order, so the valid centres of a line are a
-// contiguous row range (rows_before) and one patch x-row of NCCH consecutive
-// centres is a rectangular box of the 3-D tensor dp[row][patch row][rsg]:
-// it is fetched by ONE TMA instruction (cp.async.bulk.tensor.3d) that signals
-// an mbarrier, into a double buffer, so the copy of the next chunk overlaps
-// the arithmetic on the current one and costs no LSU issue slots.
+// contiguous row range (rows_before) and, dp being patch-row major, one patch
+// x-row of NCCH consecutive centres is one contiguous block: it is fetched by
+// ONE bulk copy on the TMA engine (cp.async.bulk) that signals an mbarrier,
+// into a double buffer, so the copy of the next chunk overlaps the arithmetic
+// on the current one and costs no LSU issue slots.
 // The gated voxels of the base line and of every partner line are covered
 // greedily by T-wide x-windows ("tiles"); a work item is a (base tile, partner
 // tile) pair within reach, i.e. T*T accumulators in registers.  For every
@@ -197,16 +198,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
         "DONE:\n"
         "}\n" :: "r"(a), "r"(parity) : "memory");
 }
-// one box {rsg, 1, NCCH} of dp -> shared memory, completion on `bar`
-__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* tmap, uint64_t* bar,
-                                            int c0, int c1, int c2)
+// one contiguous block of dp -> shared memory through the TMA engine (1-D bulk
+// copy, 16-byte aligned on both sides), completion signalled on `bar`
+__device__ __forceinline__ void bulk_load(void* smem, const void* gmem, unsigned bytes,
+                                          uint64_t* bar)
 {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5}], [%2];\n"
-        :: "r"(sa), "l"((uint64_t)tmap), "r"(ba), "r"(c0), "r"(c1), "r"(c2) : "memory");
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+        :: "r"(sa), "l"(gmem), "r"(bytes), "r"(ba) : "memory");
 }
 
 // greedy cover of the gated voxels of one line by T-wide windows; s_out gets the
@@ -248,7 +249,7 @@ __device__ int ct_tiles_of_line(const uint8_t* __restrict__ flags, const int32_t
 
 template <int NOY>
 __global__ void __launch_bounds__(CT_THREADS)
-consensus_rows_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ flags,
+consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
                       const int32_t* __restrict__ fgidx, const int32_t* __restrict__ rowvox,
                       int F, ppp_cfg cfg, const uint32_t* __restrict__ cnt,
                       float* __restrict__ cons)
@@ -270,7 +271,7 @@ consensus_rows_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* _
     __shared__ int s_npt[NOY], s_nitems;
     __shared__ __align__(8) uint64_t s_full[2];
 
-    const int line = blockIdx.x;
+    const int line = blockIdx.y;
     const int bz = line / g.Y, by = line % g.Y;
     const int64_t bline = (int64_t)line * g.X;
     const int nrows_off = (g.nz * g.ny - 1) / 2 + 1;             // offset rows >= (0,0)
@@ -286,7 +287,7 @@ consensus_rows_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* _
     bool row_ok[NOY];
 #pragma unroll
     for (int t = 0; t < NOY; t++) {
-        int orow = blockIdx.y * NOY + t;
+        int orow = blockIdx.x * NOY + t;
         int rlin = rlin_c + orow;
         oz_t[t] = rlin / g.ny - (g.psz - 1);
         oy_t[t] = rlin % g.ny - (g.psy - 1);
@@ -310,7 +311,7 @@ consensus_rows_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* _
             for (int t = 0; t < NOY; t++) {
                 const int np = s_npt[t];
                 const int16_t* pt = s_pt + t * CT_MAXTILES;
-                const bool same = (blockIdx.y * NOY + t) == 0;    // offset row (0,0)
+                const bool same = (blockIdx.x * NOY + t) == 0;    // offset row (0,0)
                 // partner windows [p0, p0+T) with some |p - b| < psx for b in [b0, b0+T)
                 while (lo[t] < np && pt[lo[t]] + T - 1 < b0 - (g.psx - 1)) lo[t]++;
                 if (hi[t] < lo[t]) hi[t] = lo[t];
@@ -393,13 +394,15 @@ consensus_rows_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* _
                 const int cz = cza + l / ncy, cy = cya + l % ncy;
                 const int q1z = bz - cz + g.rz, q1y = by - cy + g.ry;
                 float* dst = sA + buf * bufstride;
-                mbar_expect_tx(&s_full[buf], (unsigned)((1 + __popc(am)) * substride * 4));
-                tma_load_3d(dst, &tmap, &s_full[buf], 0, q1z * g.psy + q1y, c0);
+                const unsigned bytes = (unsigned)(nc * RS * 4);
+                mbar_expect_tx(&s_full[buf], (1 + __popc(am)) * bytes);
+                bulk_load(dst, dp + ((int64_t)(q1z * g.psy + q1y) * F + c0) * RS, bytes, &s_full[buf]);
 #pragma unroll
                 for (int t = 0; t < NOY; t++)
                     if (am & (1u << t))
-                        tma_load_3d(dst + (1 + t) * substride, &tmap, &s_full[buf], 0,
-                                    (q1z + oz_t[t]) * g.psy + (q1y + oy_t[t]), c0);
+                        bulk_load(dst + (1 + t) * substride,
+                                  dp + ((int64_t)((q1z + oz_t[t]) * g.psy + (q1y + oy_t[t])) * F + c0) * RS,
+                                  bytes, &s_full[buf]);
             }
             st_c += nc;
             return nc;
@@ -459,9 +462,9 @@ consensus_rows_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* _
         }
         // ---- epilogue: normalise with the integer counters and store -----------
         if (have) {
-            int rlin = rlin_c + blockIdx.y * NOY + my_t;
+            int rlin = rlin_c + blockIdx.x * NOY + my_t;
             const int kbase = rlin * g.nx - g.K - 1 + (g.psx - 1);   // k = kbase + ox
-            const bool same = (blockIdx.y * NOY + my_t) == 0;
+            const bool same = (blockIdx.x * NOY + my_t) == 0;
             int64_t pline = 0;
 #pragma unroll
             for (int t = 0; t < NOY; t++) if (my_t == t) pline = pline_t[t];
@@ -496,33 +499,6 @@ static size_t rows_smem(const Geo& g)
            (size_t)CT_MAXITEMS * 4 + (size_t)(1 + CT_NOY) * CT_MAXTILES * 2 + CT_XMAX * 2 + 128;
 }
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int make_dp_tensor_map(CUtensorMap* tm, const float* dp, int64_t F, const Geo& g)
-{
-    static PFN_encodeTiled enc = nullptr;
-    if (enc == nullptr) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
-        if (e != cudaSuccess || fn == nullptr)
-            return ppp_fail(-1, "ppp_consensus: cuTensorMapEncodeTiled unavailable");
-        enc = (PFN_encodeTiled)fn;
-    }
-    cuuint64_t dims[3] = {(cuuint64_t)g.rsg, (cuuint64_t)(g.psz * g.psy), (cuuint64_t)F};
-    cuuint64_t strides[2] = {(cuuint64_t)g.rsg * 4, (cuuint64_t)g.rp * 4};
-    cuuint32_t box[3] = {(cuuint32_t)g.rsg, 1u, (cuuint32_t)CT_NCCH};
-    cuuint32_t estr[3] = {1u, 1u, 1u};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)dp, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return ppp_fail(-1, "ppp_consensus: cuTensorMapEncodeTiled failed");
-    return 0;
-}
-
 extern "C" int64_t ppp_consensus_scratch_bytes(const ppp_cfg* cfg)
 {
     (void)cfg;
@@ -539,7 +515,7 @@ extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8
     cudaStream_t s = (cudaStream_t)stream;
     Geo g = make_geo(*cfg);
     if (impl == 1) {
-        consensus_naive_kernel<<<(unsigned)F, 128, 0, s>>>(dp, flags, fgidx, rowvox, *cfg,
+        consensus_naive_kernel<<<(unsigned)F, 128, 0, s>>>(dp, flags, fgidx, rowvox, F, *cfg,
                                                            cons, cnt);
         return ppp_check("ppp_consensus(naive)");
     }
@@ -552,16 +528,14 @@ extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8
     consensus_count_kernel<<<(unsigned)F, 256, 0, s>>>(
         (const unsigned long long*)rbits, flags, fgidx, rowvox, *cfg, cons, cnt);
     if (cfg->prod_mode == 0) return ppp_check("ppp_consensus(count)");   // no float sums needed
-    CUtensorMap tm;
-    int rc = make_dp_tensor_map(&tm, dp, F, g);
-    if (rc) return rc;
     size_t smem = rows_smem(g);
     cudaError_t e = cudaFuncSetAttribute(consensus_rows_kernel<CT_NOY>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return ppp_fail((int)e, "ppp_consensus: smem attribute");
     int nrows_off = (g.nz * g.ny - 1) / 2 + 1;
-    dim3 grid((unsigned)(g.Z * g.Y), (unsigned)((nrows_off + CT_NOY - 1) / CT_NOY));
+    // offset-row groups on x (scheduled first): the groups of one line share its A1 rows in L2
+    dim3 grid((unsigned)((nrows_off + CT_NOY - 1) / CT_NOY), (unsigned)(g.Z * g.Y));
     consensus_rows_kernel<CT_NOY><<<grid, CT_THREADS, smem, s>>>(
-        tm, flags, fgidx, rowvox, (int)F, *cfg, cnt, cons);
+        dp, flags, fgidx, rowvox, (int)F, *cfg, cnt, cons);
     return ppp_check("ppp_consensus(rows)");
 }

@@ -218,7 +218,7 @@ prepare_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags
         int po = po0 + lane;
         float d = tileD[lane][rl];
         uint8_t b = tileB[lane][rl];
-        if (dp != nullptr && po < g.P) dp[r * g.rp + dp_off(g, po)] = d;
+        if (dp != nullptr && po < g.P) dp[dp_index(g, F, r, po)] = d;
         unsigned m1 = __ballot_sync(0xffffffffu, b & 1);
         unsigned m2 = __ballot_sync(0xffffffffu, b & 2);
         if (lane == 0) {
@@ -229,7 +229,7 @@ prepare_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags
         if (dp != nullptr && blockIdx.y == 0) {
             int xr = rowvox[r] % g.X;
             for (int pr = lane; pr < g.psz * g.psy; pr += 32)
-                dp[r * g.rp + pr * g.rsg] = __int_as_float(xr);
+                dp[((int64_t)pr * F + r) * g.rsg] = __int_as_float(xr);
         }
     }
 }

@@ -33,7 +33,7 @@ __global__ void rank_fill_kernel(ppp_cfg cfg, float* __restrict__ score)
 __global__ void __launch_bounds__(RANK_THREADS)
 rank_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
             const int32_t* __restrict__ fgidx, const int32_t* __restrict__ rowvox,
-            const float* __restrict__ cons, ppp_cfg cfg, float* __restrict__ score)
+            const float* __restrict__ cons, int64_t F, ppp_cfg cfg, float* __restrict__ score)
 {
     Geo g = make_geo(cfg);
     extern __shared__ unsigned char smem_raw[];
@@ -62,7 +62,7 @@ rank_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
         int qz = 0, qy = 0, qx = 0, pv = 0;
         bool gated = false;
         if (po < g.P) {
-            d = dp[row * g.rp + dp_off(g, po)];
+            d = dp[dp_index(g, F, row, po)];
             po_decode(g, po, qz, qy, qx);
             pv = ((cz + qz - g.rz) * g.Y + (cy + qy - g.ry)) * g.X + (cx + qx - g.rx);
             gated = (flags[pv] & PPP_FLAG_GATED) != 0;
@@ -134,7 +134,7 @@ extern "C" int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fg
     if (F > 0) {
         size_t smem = (size_t)g.P * 9 + 16;
         rank_kernel<<<(unsigned)F, RANK_THREADS, smem, s>>>(dp, flags, fgidx, rowvox,
-                                                            cons, *cfg, score);
+                                                            cons, F, *cfg, score);
     }
     return ppp_check("ppp_rank");
 }
