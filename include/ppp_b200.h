@@ -164,6 +164,13 @@ int ppp_paint(const float* pred, const int32_t* nodes, int64_t m,
               const int32_t* comp, const ppp_cfg* cfg, int32_t* instances,
               void* stream);
 
+/* same with the member patches as a compact f32 [m][P] array (blockwise path:
+ * only the selected patches of a volume that does not fit the device are read,
+ * stitch_patch_graph.py:380-385). */
+int ppp_paint_patches(const float* patches, const int32_t* nodes, int64_t m,
+                      const int32_t* comp, const ppp_cfg* cfg, int32_t* instances,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

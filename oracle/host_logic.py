@@ -196,3 +196,49 @@ def assemble(pred, foreground, numinst, patchshape, kw, kern):
     out['instances'] = inst
     out['components'] = comps
     return out
+
+
+def oracle_block_fn(block, foreground, mask, numinst, **kw):
+    """do_block(..., return_intermediates=True) (vote_instances.py:455-476) on
+    the CPU oracle; honours selected_patches / selected_patch_pairs the way
+    stitch_vote_instances uses them (stitch_patch_graph.py:323-328)."""
+    from . import cpu_oracle
+    ps = np.array(kw['patchshape'])
+    rad = ps // 2
+    pred = np.ascontiguousarray(block, np.float32)
+    overlap_mask = 1 * (numinst > 1)
+    mask = mask.copy()
+    mask[overlap_mask > 0] = 0
+    radslice = tuple(slice(int(rad[i]), mask.shape[i] - int(rad[i])) for i in range(3))
+    if np.count_nonzero(mask[radslice]) == 0:
+        return None, None
+    allp = interior_patches(foreground, rad)
+    if len(allp) == 0:
+        return None, None
+    O = cpu_oracle.Oracle(pred, numinst > 1, ps, cpu_oracle.variant_from_kwargs(kw))
+    O.consensus()
+    O.norm()
+    if kw.get('selected_patch_pairs') is not None:
+        pairs = np.array(kw['selected_patch_pairs'], dtype=np.uint32).reshape(-1, 6)
+    else:
+        score = O.rank()
+        ranked = rank_by_score(allp, score)
+        fc = np.float32(kw['fc_threshold'])
+        sel = foreground_cover(overlap_mask, mask, ps, ranked, rad, pred, fc,
+                               sparse=kw['select_patches_for_sparse_data'])
+        if not kw.get('skipThinCover', False) and len(sel) > 0:
+            sel = thin_cover(mask, sel, ps, rad, pred, fc)
+        pairs = patch_pairs(sel, ps, kw['includeSinglePatchCCS'],
+                            kw.get('max_total_patch_distance_in_ps_multiples', 2))
+    if pairs is None or len(pairs) == 0:
+        return None, None
+    return pairs, O.patch_graph(pairs)
+
+
+def oracle_paint_fn(inputs, pairs, aff, rank=0, world=1, **kw):
+    """global labelling (stitch_patch_graph.py:360-399) with networkx."""
+    ps = np.array(kw['patchshape'])
+    pred = np.asarray(inputs.pred).astype(np.float32)
+    inst, _ = label_instances(pairs, aff, pred, ps, ps // 2, inputs.shape,
+                              np.float32(kw['patch_threshold']), dtype=np.uint32)
+    return inst

@@ -203,7 +203,12 @@ class RefSession:
         pc = stub('pycuda')
         pc.compiler = stub('pycuda.compiler')
         pc.driver = stub('pycuda.driver')
-        stub('numcodecs', Blosc=lambda **k: None)
+        class _Blosc:
+            BITSHUFFLE = 2
+
+            def __init__(self, **k):
+                pass
+        stub('numcodecs', Blosc=_Blosc)
         stub('colorcet')
         stub('nrrd')
 
@@ -292,3 +297,96 @@ class RefSession:
         )
         kw.update(over)
         return kw
+
+
+# ----------------------------------------------------------------------------
+# in-memory stand-ins for zarr / h5py so that the reference's blockwise driver
+# (stitch_patch_graph.py) can run unmodified without the real packages
+# ----------------------------------------------------------------------------
+class _Arr(np.ndarray):
+    """ndarray with an `.attrs` dict (zarr / h5py datasets have one)."""
+    def __new__(cls, a):
+        obj = np.asarray(a).view(cls)
+        obj.attrs = {}
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.attrs = getattr(obj, 'attrs', {})
+
+
+class FakeGroup:
+    _stores = {}
+
+    def __init__(self):
+        self.d = {}
+
+    @classmethod
+    def open(cls, path, mode='r', **kw):
+        path = os.path.abspath(path)
+        if mode == 'w' or path not in cls._stores:
+            cls._stores[path] = FakeGroup()
+            if mode in ('w', 'a') and not os.path.exists(path):
+                os.makedirs(path)          # the reference tests os.path.exists(res_file)
+        return cls._stores[path]
+
+    def _split(self, key):
+        return [k for k in key.split('/') if k]
+
+    def __contains__(self, key):
+        return any(k == '/'.join(self._split(key)) or
+                   k.startswith('/'.join(self._split(key)) + '/') for k in self.d)
+
+    def __getitem__(self, key):
+        key = '/'.join(self._split(key))
+        if key in self.d:
+            return self.d[key]
+        sub = FakeGroup()
+        sub.d = {k[len(key) + 1:]: v for k, v in self.d.items() if k.startswith(key + '/')}
+        if not sub.d:
+            raise KeyError(key)
+        return sub
+
+    def __setitem__(self, key, value):
+        self.d['/'.join(self._split(key))] = _Arr(value)
+
+    def keys(self):
+        return sorted({k.split('/')[0] for k in self.d})
+
+    def create_dataset(self, name, data=None, shape=None, dtype=None, **kw):
+        arr = np.array(data, dtype=dtype) if data is not None else np.zeros(shape, dtype)
+        self[name] = arr
+        return self['/'.join(self._split(name))]
+
+    create = create_dataset
+
+    def close(self):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def install_fake_io():
+    """replace the zarr / h5py stubs by the in-memory stores above."""
+    z = sys.modules['zarr']
+    z.open = FakeGroup.open
+    h = sys.modules['h5py']
+    h.File = lambda path, mode='r', **kw: FakeGroup.open(path, mode)
+    pc = sys.modules['pycuda']
+    auto = types.ModuleType('pycuda.autoinit')
+    auto.context = None
+    auto._ppp_stub = True
+    sys.modules['pycuda.autoinit'] = auto
+    pc.autoinit = auto
+
+
+def load_stitch_module(session):
+    """import the reference's stitch_patch_graph.py under the synthetic package
+    (needs the fake IO) and patch its device boundary like the other modules."""
+    install_fake_io()
+    for n in ('io_hdflike', 'stitch_patch_graph'):
+        session.mods[n] = importlib.import_module('ppp_ref.vote_instances.' + n)
+    return session.mods['stitch_patch_graph']

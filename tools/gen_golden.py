@@ -202,7 +202,58 @@ class Recorder:
             self.d['pairs'] = np.array(arrs[3])
 
 
+def run_blockwise(S):
+    """the reference's blockwise driver (stitch_patch_graph.main) on an
+    in-memory zarr stand-in (oracle/ref_runner.FakeGroup)."""
+    import shutil
+    sp = ref_runner.load_stitch_module(S)
+    ps = np.array([5, 5, 5])
+    skw = dict(kind='neurites', seed=21, shape=(24, 44, 44), n=6, radius=(1.5, 2.5),
+               seg_len=9.0, n_seg=8)
+    pred, numinst, labels = synth.make_case(patchshape=ps, **skw)
+    root = '/tmp/ppp_gold_blk'
+    shutil.rmtree(root, ignore_errors=True)
+    pred_path = os.path.join(root, 'sample.zarr')
+    store = ref_runner.FakeGroup.open(pred_path, 'w')
+    store['volumes/pred_affs'] = pred.astype(np.float16)
+    prob = np.stack([(numinst == 0), (numinst == 1), (numinst > 1)]).astype(np.float32)
+    store['volumes/pred_numinst'] = prob
+    kw = S.default_kwargs(
+        blockwise=True, chunksize=[12, 22, 22], patchshape=[5, 5, 5],
+        aff_key='volumes/pred_affs', numinst_key='volumes/pred_numinst', fg_key=None,
+        numinst_threshs=[0.9, 0.1], only_bb=False, output_format='hdf',
+        num_parallel_blocks=1, ignore_small_comps=0, skeletonize_foreground=False,
+        remove_small_comps=0, res_key='vote_instances')
+    del kw['result_folder']
+    t0 = time.time()
+    sp.main(pred_path, result_folder=os.path.join(root, 'out'), **kw)
+    dt = time.time() - t0
+    out = ref_runner.FakeGroup.open(os.path.join(root, 'out', 'sample.hdf'))
+    blk = ref_runner.FakeGroup.open(os.path.join(root, 'out', 'sample.zarr'))
+    import hashlib
+    res = dict(
+        pred_sha1=hashlib.sha1(pred.astype(np.float16).tobytes()).hexdigest(),
+        numinst=numinst, patchshape=ps.astype(np.int32),
+        kwargs=json.dumps({k: v for k, v in kw.items()
+                           if isinstance(v, (bool, int, float, str, list)) or v is None}),
+        synth=json.dumps({k: (list(v) if isinstance(v, tuple) else v) for k, v in skw.items()}),
+        instances=np.asarray(out['vote_instances']),
+        foreground=np.asarray(out['vote_foreground']),
+    )
+    for k, v in blk.d.items():
+        res['blk/' + k.replace('volumes/blocks/', '')] = np.asarray(v)
+    fn = os.path.join(GOLD, 'blockwise3d_ps5.npz')
+    np.savez_compressed(fn, **res)
+    print('%-24s %6.1fs  blocks+faces=%d inst=%d  %.2f MB' % (
+        'blockwise3d_ps5', dt, len(blk.d) // 2, len(np.unique(res['instances'])) - 1,
+        os.path.getsize(fn) / 1e6))
+
+
 def main():
+    if sys.argv[1:] == ['blockwise']:
+        S = ref_runner.RefSession()
+        run_blockwise(S)
+        return 0
     names = sys.argv[1:] or list(CASES)
     rec = Recorder()
     S = ref_runner.RefSession(recorder=rec)
