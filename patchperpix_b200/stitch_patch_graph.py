@@ -302,7 +302,7 @@ def paint_global(inputs, pairs, aff, rank=0, world=1, **kwargs):
     ps = np.asarray(kwargs['patchshape'])
     shape = inputs.shape
     dev = torch.device('cuda', torch.cuda.current_device())
-    cfg = cc.make_cfg(shape, ps, **kwargs)
+    cfg = cc.make_cfg(shape, ps, **{k: v for k, v in kwargs.items() if k != 'patchshape'})
     V = int(np.prod(shape))
     stream = cc.current_stream_ptr()
     pd = torch.from_numpy(pairs.view(np.int32)).to(dev)
