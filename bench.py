@@ -44,7 +44,7 @@ KW = dict(patch_threshold=0.5, fc_threshold=0.5, cuda=True, blockwise=False,
           overlapping_inst=True, skipThinCover=False)
 # kernels launched per C-ABI call (counted to report gpu_launches)
 LAUNCHES = dict(ppp_gate=1, ppp_compact=3, ppp_prepare_patches=2, ppp_consensus=3,
-                ppp_rank=2, ppp_rank_sort=5, ppp_cover=1, ppp_thin=1, ppp_patch_graph=1,
+                ppp_rank=3, ppp_rank_sort=5, ppp_cover=1, ppp_thin=1, ppp_patch_graph=1,
                 ppp_label_cc=9, ppp_paint=1)
 
 

@@ -64,7 +64,9 @@ typedef struct ppp_cfg {
     int32_t prod_mode;          /* 0 vote counter, 1 PROB_PRODUCT, 2 NORM_PROB_PRODUCT */
     int32_t norm_aff;           /* consensus_norm_aff: divide sums by vote count */
     int32_t use_overlap;        /* -DOVERLAP */
-    int32_t rank_flags;         /* bit0 NORM_PATCH_RANK, bit1 COUNT_POS_NEG */
+    int32_t rank_flags;         /* bit0 NORM_PATCH_RANK, bit1 COUNT_POS_NEG, bit2 fast
+                                   parallel double sum instead of the reference's serial
+                                   float order (scores then differ by its rounding) */
     int32_t graph_flags;        /* bit0 NORM_PATCH_AFFINITY */
     int32_t reserved;
 } ppp_cfg;
@@ -111,9 +113,10 @@ int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8_t* flags,
 
 /* ---- step 2: rank (rankPatches.cu) ----------------------------------------
  * score f32 [Z][Y][X]: border voxels -1 / -9999999, non-fg interior 0. */
+int64_t ppp_rank_scratch_bytes(const ppp_cfg* cfg, int64_t F);
 int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fgidx,
              const int32_t* rowvox, int64_t F, const float* cons,
-             const ppp_cfg* cfg, float* score, void* stream);
+             const ppp_cfg* cfg, float* score, void* scratch, void* stream);
 /* stable descending sort of the candidate voxels by score
  * (ranked_patches.py:21-30): cand[n] voxel indices in raster order ->
  * order[n] = candidate voxel indices, best first.  scratch from

@@ -107,9 +107,11 @@ class BlockAssembler:
         """rank_patches_cuda (ranked_patches.py:33-74): score volume."""
         torch = _torch()
         self.score = torch.empty(self.shape, dtype=torch.float32, device=self.dev)
+        scratch = torch.empty(cc.call('ppp_rank_scratch_bytes', self.cfg, self.F),
+                              dtype=torch.uint8, device=self.dev)
         cc.call('ppp_rank', cc.ptr(self.dp), cc.ptr(self.flags), cc.ptr(self.fgidx),
                 cc.ptr(self.rowvox), self.F, cc.ptr(self.cons), self.cfg,
-                cc.ptr(self.score), self.stream)
+                cc.ptr(self.score), cc.ptr(scratch), self.stream)
         return self.score
 
     def candidates(self):

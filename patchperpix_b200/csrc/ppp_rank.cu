@@ -124,19 +124,234 @@ rank_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
     }
 }
 
+// ---------------------------------------------------------------------------
+// reference-order ranking.  rankPatches.cu accumulates its ~P^2/2 terms in ONE
+// float, serially; for large patches the rounding of that running sum is
+// systematic (1e-3 relative at 41x41) and decides the rank order, hence the
+// cover, hence the labels.  To stay label-identical these kernels reproduce the
+// exact sequence of float additions of the reference's loop nest (po1 over the
+// high pixels, po2 over the other gated pixels):
+//   rank_lists_kernel  compacts, per patch centre, the voting pixels (in po
+//                      order) and the sub-list of high pixels into scratch;
+//   rank_ref_kernel    one WARP owns RR_CPW centres.  Lane s < RR_CPW performs
+//                      the serial float adds of centre s; the values are
+//                      gathered by the whole warp, 32 consecutive terms of one
+//                      centre per coalesced request (all RR_CPW requests in
+//                      flight together), and handed over through a
+//                      transposition buffer.  Skipped terms are fed as +0.0f,
+//                      which leaves a float sum unchanged.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+rank_lists_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
+                  const int32_t* __restrict__ rowvox, int64_t F, ppp_cfg cfg,
+                  uint16_t* __restrict__ lists, uint16_t* __restrict__ hlists,
+                  int32_t* __restrict__ meta)
+{
+    Geo g = make_geo(cfg);
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= F) return;
+    const int vc = rowvox[row];
+    int n = 0, nH = 0, nG = 0;
+    if (flags[vc] & PPP_FLAG_CENTRE) {
+        int cz, cy, cx;
+        vox_decode(g, vc, cz, cy, cx);
+        for (int base = 0; base < g.P; base += 32) {
+            int po = base + lane;
+            float d = 0.0f;
+            bool gated = false;
+            if (po < g.P) {
+                int qz, qy, qx;
+                po_decode(g, po, qz, qy, qx);
+                d = dp[dp_index(g, F, row, po)];
+                int pv = ((cz + qz - g.rz) * g.Y + (cy + qy - g.ry)) * g.X + (cx + qx - g.rx);
+                gated = (flags[pv] & PPP_FLAG_GATED) != 0;
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, d != 0.0f);
+            unsigned balh = __ballot_sync(0xffffffffu, d > 0.0f);
+            unsigned lt = (1u << lane) - 1u;
+            if (d != 0.0f) {
+                int idx = n + __popc(bal & lt);
+                lists[row * g.P + idx] = (uint16_t)(po | (d > 0.0f ? 0x8000 : 0));
+                if (d > 0.0f) hlists[row * g.P + nH + __popc(balh & lt)] = (uint16_t)idx;
+            }
+            n += __popc(bal);
+            nH += __popc(balh);
+            nG += __popc(__ballot_sync(0xffffffffu, gated));
+        }
+    } else n = -1;
+    if (lane == 0) { meta[row * 4] = n; meta[row * 4 + 1] = nH; meta[row * 4 + 2] = nG; }
+}
+
+#define RR_WARPS 4
+#define RR_CPW 8
+
+__global__ void __launch_bounds__(RR_WARPS * 32)
+rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
+                const int32_t* __restrict__ rowvox, const float* __restrict__ cons,
+                const uint16_t* __restrict__ lists, const uint16_t* __restrict__ hlists,
+                const int32_t* __restrict__ meta, int64_t F, ppp_cfg cfg,
+                float* __restrict__ score)
+{
+    Geo g = make_geo(cfg);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* tab_dv = (int32_t*)smem_raw;                       // [P] voxel delta of patch pixel
+    uint16_t* tab_lin = (uint16_t*)(tab_dv + g.P);              // [P] position in the offset raster
+    float* stage = (float*)(tab_lin + g.P + (g.P & 1));         // [RR_WARPS][RR_CPW][33]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int po = threadIdx.x; po < g.P; po += blockDim.x) {
+        int qz, qy, qx;
+        po_decode(g, po, qz, qy, qx);
+        tab_dv[po] = ((qz - g.rz) * g.Y + (qy - g.ry)) * g.X + (qx - g.rx);
+        tab_lin[po] = (uint16_t)po_lin(g, qz, qy, qx);
+    }
+    __syncthreads();
+    float* mystage = stage + w * RR_CPW * 33;
+    const bool count_mode = (cfg.rank_flags & 2) != 0;
+    const int64_t ngroups = (F + RR_CPW - 1) / RR_CPW;
+
+    for (int64_t grp = (int64_t)blockIdx.x * RR_WARPS + w; grp < ngroups;
+         grp += (int64_t)gridDim.x * RR_WARPS) {
+        // lane s < RR_CPW owns centre row grp*RR_CPW + s
+        const int64_t myrow = grp * RR_CPW + lane;
+        int n_s = -1, nH_s = 0, nG_s = 0, vc_s = 0;
+        if (lane < RR_CPW && myrow < F) {
+            n_s = meta[myrow * 4]; nH_s = meta[myrow * 4 + 1]; nG_s = meta[myrow * 4 + 2];
+            vc_s = rowvox[myrow];
+        }
+        float acc = 0.0f;                 // running float sum of my centre
+        int cur_h = 0, cur_t = 0;         // current high row (index into hlist) and slot
+        int cur_i = 0, cur_li = 0;        // its list index and raster position
+        int64_t cur_row = 0;              // its consensus row base
+        bool alive = n_s > 0 && nH_s > 0;
+        if (alive) {
+            cur_i = hlists[myrow * g.P];
+            int ei = lists[myrow * g.P + cur_i] & 0x7fff;
+            cur_li = tab_lin[ei];
+            cur_row = (int64_t)fgidx[vc_s + tab_dv[ei]] * g.K;
+        }
+        while (true) {
+            const unsigned live = __ballot_sync(0xffffffffu, alive);
+            if (!live) break;
+            // ---- gather 32 consecutive terms of every live centre, in three phases
+            // (list entries, consensus values, hand-over) so that RR_CPW independent
+            // loads are in flight per lane ---------------------------------------------
+            int after_[RR_CPW], li_[RR_CPW], ej_[RR_CPW], vc_[RR_CPW];
+            int64_t row_[RR_CPW];
+            bool ok_[RR_CPW];
+            float val_[RR_CPW];
+#pragma unroll
+            for (int u = 0; u < RR_CPW; u++) {
+                const int i = __shfl_sync(0xffffffffu, cur_i, u);
+                const int t0 = __shfl_sync(0xffffffffu, cur_t, u);
+                const int n = __shfl_sync(0xffffffffu, n_s, u);
+                li_[u] = __shfl_sync(0xffffffffu, cur_li, u);
+                row_[u] = __shfl_sync(0xffffffffu, cur_row, u);
+                vc_[u] = __shfl_sync(0xffffffffu, vc_s, u);
+                const int tt = t0 + lane;
+                ok_[u] = ((live >> u) & 1u) && tt < n - 1;
+                const int j = tt < i ? tt : tt + 1;
+                after_[u] = j > i;
+                ej_[u] = ok_[u] ? lists[(grp * RR_CPW + u) * g.P + j] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < RR_CPW; u++) {
+                const int pj = ej_[u] & 0x7fff;
+                const bool hj = (ej_[u] & 0x8000) != 0;
+                const int lj = tab_lin[pj];
+                float v3 = 0.0f;
+                if (ok_[u]) {
+                    if (after_[u]) v3 = cons[row_[u] + lj - li_[u] - 1];
+                    else if (!hj)
+                        v3 = cons[(int64_t)fgidx[vc_[u] + tab_dv[pj]] * g.K + li_[u] - lj - 1];
+                }
+                val_[u] = v3;
+            }
+#pragma unroll
+            for (int u = 0; u < RR_CPW; u++) {
+                const bool hj = (ej_[u] & 0x8000) != 0;
+                float v3 = val_[u], val = 0.0f;
+                if (ok_[u]) {
+                    if (after_[u]) {
+                        // rankPatches.cu:88-100 (both high) / :102-137 (high, background)
+                        if (count_mode) v3 = (v3 != 0.0f) ? copysignf(1.0f, v3) : (hj ? -1.0f : 1.0f);
+                        val = hj ? v3 : -v3;
+                    } else if (!hj) {
+                        // background pixel before the high one: reversed slot (:109-126)
+                        if (count_mode) v3 = (v3 != 0.0f) ? copysignf(1.0f, v3) : 1.0f;
+                        val = -v3;
+                    }
+                }
+                mystage[u * 33 + lane] = val;
+            }
+            __syncwarp();
+            // ---- serial float adds of my centre, in the reference's order --------------
+            if (alive) {
+                const float* st = mystage + lane * 33;
+#pragma unroll
+                for (int q = 0; q < 32; q++) acc += st[q];
+                cur_t += 32;
+                if (cur_t >= n_s - 1) {                         // next high row
+                    cur_t = 0;
+                    cur_h++;
+                    if (cur_h >= nH_s) alive = false;
+                    else {
+                        cur_i = hlists[myrow * g.P + cur_h];
+                        int ei = lists[myrow * g.P + cur_i] & 0x7fff;
+                        cur_li = tab_lin[ei];
+                        cur_row = (int64_t)fgidx[vc_s + tab_dv[ei]] * g.K;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (n_s >= 0) {
+            unsigned h = (unsigned)nH_s, gg = (unsigned)nG_s;
+            unsigned fgCnt = h * gg - h - (h * (h - 1)) / 2;
+            score[vc_s] = (cfg.rank_flags & 1) ? acc / (float)(fgCnt > 1 ? fgCnt : 1) : acc;
+        }
+    }
+}
+
+extern "C" int64_t ppp_rank_scratch_bytes(const ppp_cfg* cfg, int64_t F)
+{
+    Geo g = make_geo(*cfg);
+    if (F < 1) F = 1;
+    return 2 * ((F * g.P * 2 + 255) / 256) * 256 + ((F * 16 + 255) / 256) * 256 + 256;
+}
+
 extern "C" int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fgidx,
                         const int32_t* rowvox, int64_t F, const float* cons,
-                        const ppp_cfg* cfg, float* score, void* stream)
+                        const ppp_cfg* cfg, float* score, void* scratch, void* stream)
 {
     Geo g = make_geo(*cfg);
     cudaStream_t s = (cudaStream_t)stream;
     rank_fill_kernel<<<(unsigned)((g.V + 255) / 256), 256, 0, s>>>(*cfg, score);
-    if (F > 0) {
+    if (F <= 0) return ppp_check("ppp_rank");
+    if (cfg->rank_flags & 4) {
+        // fast path: parallel sum in double (NOT the reference's rounding)
         size_t smem = (size_t)g.P * 9 + 16;
         rank_kernel<<<(unsigned)F, RANK_THREADS, smem, s>>>(dp, flags, fgidx, rowvox,
                                                             cons, F, *cfg, score);
+        return ppp_check("ppp_rank(fast)");
     }
-    return ppp_check("ppp_rank");
+    if (g.P >= 32768) return ppp_fail(-1, "ppp_rank: patch too large");
+    if (scratch == nullptr) return ppp_fail(-1, "ppp_rank: scratch required");
+    size_t lb = ((F * g.P * 2 + 255) / 256) * 256;
+    uint16_t* lists = (uint16_t*)scratch;
+    uint16_t* hlists = (uint16_t*)((char*)scratch + lb);
+    int32_t* meta = (int32_t*)((char*)scratch + 2 * lb);
+    rank_lists_kernel<<<(unsigned)((F + 3) / 4), 128, 0, s>>>(dp, flags, rowvox, F, *cfg, lists,
+                                                              hlists, meta);
+    size_t smem = (size_t)g.P * 4 + (size_t)(g.P + 1) * 2 + (size_t)RR_WARPS * RR_CPW * 33 * 4 + 32;
+    cudaError_t e = cudaFuncSetAttribute(rank_ref_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return ppp_fail((int)e, "ppp_rank: smem attribute");
+    int64_t ngroups = (F + RR_CPW - 1) / RR_CPW;
+    int64_t nblk = (ngroups + RR_WARPS - 1) / RR_WARPS;
+    rank_ref_kernel<<<(unsigned)nblk, RR_WARPS * 32, smem, s>>>(flags, fgidx, rowvox, cons, lists,
+                                                               hlists, meta, F, *cfg, score);
+    return ppp_check("ppp_rank(reference order)");
 }
 
 // ---------------------------------------------------------------------------

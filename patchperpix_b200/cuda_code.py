@@ -92,7 +92,8 @@ def make_cfg(shape, patchshape, **kwargs):
     c.norm_aff = 1 if kwargs.get('consensus_norm_aff', True) else 0
     c.use_overlap = 1 if kwargs.get('overlapping_inst', False) else 0
     c.rank_flags = (1 if kwargs.get('rank_norm_patch_score', True) else 0) | \
-                   (2 if kwargs.get('rank_int_counter', False) else 0)
+                   (2 if kwargs.get('rank_int_counter', False) else 0) | \
+                   (4 if kwargs.get('ppp_rank_fast', False) else 0)
     c.graph_flags = 1 if kwargs.get('patch_graph_norm_aff', True) else 0
     return c
 
@@ -107,7 +108,8 @@ _SIGS = {
     'ppp_prepare_patches': (ctypes.c_int, ['p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p', 'p', 'p']),
     'ppp_consensus_scratch_bytes': (ctypes.c_int64, ['cfg']),
     'ppp_consensus': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'i32', 'p', 'p']),
-    'ppp_rank': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
+    'ppp_rank_scratch_bytes': (ctypes.c_int64, ['cfg', 'i64']),
+    'ppp_rank': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'p', 'cfg', 'p', 'p', 'p']),
     'ppp_rank_sort_scratch_bytes': (ctypes.c_int64, ['i64']),
     'ppp_rank_sort': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'p', 'p']),
     'ppp_cover_scratch_bytes': (ctypes.c_int64, ['cfg']),
