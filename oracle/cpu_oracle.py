@@ -127,12 +127,14 @@ class Oracle:
             _p(score))
         return score
 
-    def patch_graph(self, pairs, cons=None):
+    def patch_graph(self, pairs, cons=None, exact_sum=False):
+        """exact_sum: accumulate in double (the reference's float accumulator
+        drifts by ~1e-3 relative at 41x41; diagnostic reference value)."""
         cons = self.cons if cons is None else cons
         pairs = np.ascontiguousarray(pairs, np.uint32)
         aff = np.zeros(len(pairs), np.float32)
         lib().ppp_oracle_patch_graph(
             ctypes.byref(self.cfg), _p(self.pred), _p(self.fgidx), _p(cons),
             _p(pairs), ctypes.c_int64(len(pairs)),
-            ctypes.c_int(self.var['graph_flags']), _p(aff))
+            ctypes.c_int(self.var['graph_flags'] | (4 if exact_sum else 0)), _p(aff))
         return aff

@@ -275,6 +275,7 @@ void ppp_oracle_patch_graph(const ppp_oracle_cfg* c, const float* pred,
                        (uint32_t)idy2 * (uint32_t)idx * (uint32_t)idx2;
         int64_t vc1 = vox(c, idz, idy, idx), vc2 = vox(c, idz2, idy2, idx2);
         float acc = 0.0f;
+        double dacc = 0.0;      /* flags bit2: exact-ish sum, diagnostic only */
         unsigned fgCnt = 0;
         for (int pz1 = 0; pz1 < PSZ; pz1++)
         for (int py1 = 0; py1 < PSY; py1++)
@@ -305,17 +306,20 @@ void ppp_oracle_patch_graph(const ppp_oracle_cfg* c, const float* pred,
                     int zo = z2 - z1 + PSZ - 1, yo = y2 - y1 + PSY - 1, xo = x2 - x1 + PSX - 1;
                     if (zo < 0 || zo >= 2 * PSZ || yo < 0 || yo >= 2 * PSY ||
                         xo < 0 || xo >= 2 * PSX) continue;
-                    acc += cons_at(c, cons, fgidx, K, v1i, z2 - z1, y2 - y1, x2 - x1);
+                    { float v3 = cons_at(c, cons, fgidx, K, v1i, z2 - z1, y2 - y1, x2 - x1);
+                      acc += v3; dacc += v3; }
                     fgCnt += 1;
                 } else {
                     int zo = z1 - z2 + PSZ - 1, yo = y1 - y2 + PSY - 1, xo = x1 - x2 + PSX - 1;
                     if (zo < 0 || zo >= 2 * PSZ || yo < 0 || yo >= 2 * PSY ||
                         xo < 0 || xo >= 2 * PSX) continue;
-                    acc += cons_at(c, cons, fgidx, K, v2i, z1 - z2, y1 - y2, x1 - x2);
+                    { float v3 = cons_at(c, cons, fgidx, K, v2i, z1 - z2, y1 - y2, x1 - x2);
+                      acc += v3; dacc += v3; }
                     fgCnt += 1;
                 }
             }
         }
+        if (flags & 4) acc = (float)dacc;
         if (flags & 1) aff[id1] = acc / (float)(fgCnt > 1 ? fgCnt : 1);
         else aff[id1] = acc;
     }

@@ -184,7 +184,7 @@ rank_lists_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flag
 }
 
 #define RR_WARPS 4
-#define RR_CPW 8
+#define RR_CPW 4
 
 __global__ void __launch_bounds__(RR_WARPS * 32)
 rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
