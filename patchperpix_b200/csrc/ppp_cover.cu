@@ -11,24 +11,26 @@
 
 struct BitVol {
     uint32_t* w;      // [Z*Y][WX]
-    int WX;           // words per x-row incl. one guard word
+    int WX;           // words per x-row
 };
 
-__host__ __device__ inline int bitvol_wx(int X) { return (X + 31) / 32 + 1; }
+__host__ __device__ inline int bitvol_wx(int X) { return (X + 31) / 32; }
 
 // 32 mask bits starting at bit position `bit` of x-row `r`
 __device__ __forceinline__ uint32_t bv_get32(const BitVol& b, int r, int bit)
 {
-    const uint32_t* p = b.w + (int64_t)r * b.WX + (bit >> 5);
-    return __funnelshift_r(p[0], p[1], bit & 31);
+    const int wi = bit >> 5;
+    const uint32_t* p = b.w + (int64_t)r * b.WX + wi;
+    return __funnelshift_r(p[0], (wi + 1 < b.WX) ? p[1] : 0u, bit & 31);
 }
 
 __device__ __forceinline__ void bv_clear32(const BitVol& b, int r, int bit, uint32_t m)
 {
-    uint32_t* p = b.w + (int64_t)r * b.WX + (bit >> 5);
+    const int wi = bit >> 5;
+    uint32_t* p = b.w + (int64_t)r * b.WX + wi;
     int s = bit & 31;
     p[0] &= ~(m << s);
-    if (s) p[1] &= ~(m >> (32 - s));
+    if (s && wi + 1 < b.WX) p[1] &= ~(m >> (32 - s));
 }
 
 // 32 bits of a patch bit string starting at bit `bit` (zero past the end)
@@ -111,8 +113,8 @@ extern "C" int64_t ppp_cover_scratch_bytes(const ppp_cfg* cfg)
 }
 
 #define COVER_THREADS 1024
-#define THIN_THREADS 256
-#define SMEM_BITVOL_MAX (200 * 1024)
+#define THIN_THREADS 1024
+#define SMEM_BITVOL_MAX (192 * 1024)
 
 // ---------------------------------------------------------------------------
 // greedy cover (foreground_cover.py:111-180).  A patch is selected iff it
@@ -135,6 +137,9 @@ cover_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ overl
     extern __shared__ uint32_t s_bits[];
     __shared__ int s_remaining;
     __shared__ int s_cnt[COVER_THREADS];
+    __shared__ int16_t s_surv[COVER_THREADS];
+    __shared__ int s_nsurv, s_cnt2[32], s_vc[32];
+    uint32_t* s_fc = s_bits + (use_smem ? (size_t)g.Z * g.Y * bitvol_wx(g.X) : 0);   // [32][W]
     BitVol bv;
     bv.WX = bitvol_wx(g.X);
     bv.w = use_smem ? s_bits : gbits;
@@ -164,28 +169,73 @@ cover_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ overl
                 if (lane == 0) s_cnt[i] = cnt;
             }
             __syncthreads();
-            // phase B: serial replay of the survivors
+            // phase B: replay of the survivors in rank order.  Sub-batches of up to 32
+            // survivors: every warp stages the bit string of one survivor in shared
+            // memory and re-counts it against the live mask in parallel; warp 0 then
+            // walks the sub-batch in order, and only a survivor whose window overlaps
+            // a patch selected earlier in the same sub-batch is counted again.
+            if (threadIdx.x == 0) s_nsurv = 0;
+            __syncthreads();
             if (w == 0) {
-                int remaining = s_remaining;
-                for (int i = 0; i < COVER_THREADS && remaining > 0; i++) {
-                    if (s_cnt[i] <= pix_th) continue;
-                    int64_t r = r0 + i;
-                    int vc = order[r];
-                    int cz, cy, cx;
-                    vox_decode(g, vc, cz, cy, cx);
-                    const uint32_t* pm = fcmask + (int64_t)fgidx[vc] * g.W;
-                    int cnt = patch_window_count<false>(g, bv, pm, cz, cy, cx, lane, nullptr);
-                    if (cnt > pix_th) {
-                        int rc = 0;
-                        patch_window_count<true>(g, bv, pm, cz, cy, cx, lane, &rc);
-                        __syncwarp();
-                        remaining -= warp_sum_i(rc);
-                        if (lane == 0) selected[r] = 1;
-                    }
+                int nsv = 0;
+                for (int base = 0; base < COVER_THREADS; base += 32) {
+                    bool sv = s_cnt[base + lane] > pix_th;
+                    unsigned bal = __ballot_sync(0xffffffffu, sv);
+                    if (sv) s_surv[nsv + __popc(bal & ((1u << lane) - 1u))] = (int16_t)(base + lane);
+                    nsv += __popc(bal);
                 }
-                if (lane == 0) s_remaining = remaining;
+                if (lane == 0) s_nsurv = nsv;
             }
             __syncthreads();
+            const int nsurv = s_nsurv;
+            for (int sb = 0; sb < nsurv; sb += 32) {
+                if (s_remaining <= 0) break;
+                const int nb = min(32, nsurv - sb);
+                if (w < nb) {
+                    const int64_t r = r0 + s_surv[sb + w];
+                    const int vc = order[r];
+                    const uint32_t* pm = fcmask + (int64_t)fgidx[vc] * g.W;
+                    for (int q = lane; q < g.W; q += 32) s_fc[w * g.W + q] = pm[q];
+                    __syncwarp();
+                    int cz, cy, cx;
+                    vox_decode(g, vc, cz, cy, cx);
+                    int cnt = patch_window_count<false>(g, bv, s_fc + w * g.W, cz, cy, cx, lane,
+                                                        nullptr);
+                    if (lane == 0) { s_cnt2[w] = cnt; s_vc[w] = vc; }
+                }
+                __syncthreads();
+                if (w == 0) {
+                    int remaining = s_remaining;
+                    unsigned stale = 0;                          // survivors to count again
+                    for (int k = 0; k < nb && remaining > 0; k++) {
+                        const int vc = s_vc[k];
+                        int cz, cy, cx;
+                        vox_decode(g, vc, cz, cy, cx);
+                        const uint32_t* pm = s_fc + k * g.W;
+                        int cnt = s_cnt2[k];
+                        if ((stale >> k) & 1u)
+                            cnt = patch_window_count<false>(g, bv, pm, cz, cy, cx, lane, nullptr);
+                        if (cnt > pix_th) {
+                            int rc = 0;
+                            patch_window_count<true>(g, bv, pm, cz, cy, cx, lane, &rc);
+                            __syncwarp();
+                            remaining -= warp_sum_i(rc);
+                            if (lane == 0) selected[r0 + s_surv[sb + k]] = 1;
+                            // later survivors whose window intersects this one are stale
+                            bool hit = false;
+                            if (lane > k && lane < nb) {
+                                int oz, oy, ox;
+                                vox_decode(g, s_vc[lane], oz, oy, ox);
+                                hit = abs(oz - cz) < g.psz && abs(oy - cy) < g.psy &&
+                                      abs(ox - cx) < g.psx;
+                            }
+                            stale |= __ballot_sync(0xffffffffu, hit);
+                        }
+                    }
+                    if (lane == 0) s_remaining = remaining;
+                }
+                __syncthreads();
+            }
         }
         if (s_remaining < 1) break;                                  // :50-51
     }
@@ -200,11 +250,11 @@ extern "C" int ppp_cover(const uint8_t* mask, const uint8_t* overlap, const int3
     Geo g = make_geo(*cfg);
     size_t bytes = (size_t)g.Z * g.Y * bitvol_wx(g.X) * 4;
     int use_smem = bytes <= SMEM_BITVOL_MAX;
-    size_t smem = use_smem ? bytes : 0;
-    if (use_smem) {
+    size_t smem = (use_smem ? bytes : 0) + (size_t)32 * g.W * 4;
+    {
         cudaError_t e = cudaFuncSetAttribute(cover_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             SMEM_BITVOL_MAX);
+                                             SMEM_BITVOL_MAX + 12 * 1024);
         if (e != cudaSuccess) return ppp_fail((int)e, "ppp_cover: smem attribute");
     }
     cover_kernel<<<1, COVER_THREADS, smem, (cudaStream_t)stream>>>(
