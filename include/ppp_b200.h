@@ -174,6 +174,22 @@ int ppp_paint_patches(const float* patches, const int32_t* nodes, int64_t m,
                       const int32_t* comp, const ppp_cfg* cfg, int32_t* instances,
                       void* stream);
 
+/* ---- ppp+dec: code -> patch decoder on the tensor cores --------------------
+ * (experiments/flylight/setups/setup01/decode.py:16-65 + Autoencoder.forward,
+ * torch_model.py:523-544; flylight sizes: code 176 = 22 x 2^3, patch 7^3).
+ * codes f32 [B][176]; patches f32 [B][343] (logits, or sigmoid if requested).
+ * Weights (device): w_fc f32 [128][22]; w_up0 fp16 [27][2][64][64], w_c0a,
+ * w_c0b fp16 [27][1][64][64] = [tap][cin chunk][cout][cin]; biases f32 [64];
+ * w_up1 f32 [64][27]; w_c1a, w_c1b f32 [27]; scalar biases f32 [1].
+ * scratch: ppp_decode_scratch_bytes(B). */
+int64_t ppp_decode_scratch_bytes(int64_t B);
+int ppp_decode(const float* codes, int64_t B, const float* w_fc, const float* b_fc,
+               const void* w_up0, const float* b_up0, const void* w_c0a,
+               const float* b_c0a, const void* w_c0b, const float* b_c0b,
+               const float* w_up1, const float* b_up1, const float* w_c1a,
+               const float* b_c1a, const float* w_c1b, const float* b_c1b,
+               int32_t apply_sigmoid, float* patches, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

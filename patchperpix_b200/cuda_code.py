@@ -121,6 +121,8 @@ _SIGS = {
     'ppp_label_cc': (ctypes.c_int, ['p', 'p', 'i64', 'cfg', 'p', 'p', 'p', 'p']),
     'ppp_paint': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
     'ppp_paint_patches': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
+    'ppp_decode_scratch_bytes': (ctypes.c_int64, ['i64']),
+    'ppp_decode': (ctypes.c_int, ['p', 'i64'] + ['p'] * 14 + ['i32', 'p', 'p', 'p']),
 }
 _CT = {'p': ctypes.c_void_p, 'i64': ctypes.c_int64, 'i32': ctypes.c_int32,
        'cfg': ctypes.POINTER(PppCfg)}
