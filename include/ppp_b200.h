@@ -180,13 +180,15 @@ int ppp_paint_patches(const float* patches, const int32_t* nodes, int64_t m,
  * codes f32 [B][176]; patches f32 [B][343] (logits, or sigmoid if requested).
  * Weights (device): w_fc f32 [128][22]; w_up0 fp16 [27][2][64][64], w_c0a,
  * w_c0b fp16 [27][1][64][64] = [tap][cin chunk][cout][cin]; biases f32 [64];
- * w_up1 f32 [64][27]; w_c1a, w_c1b f32 [27]; scalar biases f32 [1].
+ * w_up1 fp16 [27][1][16][64]: the last up-sampling layer (nearest x2 + 3^3 conv
+ * 64->1) folded into one conv per output parity (row p < 8, rows 8..15 zero);
+ * w_c1a, w_c1b f32 [27]; scalar biases f32 [1].
  * scratch: ppp_decode_scratch_bytes(B). */
 int64_t ppp_decode_scratch_bytes(int64_t B);
 int ppp_decode(const float* codes, int64_t B, const float* w_fc, const float* b_fc,
                const void* w_up0, const float* b_up0, const void* w_c0a,
                const float* b_c0a, const void* w_c0b, const float* b_c0b,
-               const float* w_up1, const float* b_up1, const float* w_c1a,
+               const void* w_up1, const float* b_up1, const float* w_c1a,
                const float* b_c1a, const float* w_c1b, const float* b_c1b,
                int32_t apply_sigmoid, float* patches, void* scratch, void* stream);
 

@@ -10,9 +10,13 @@
 //   crop 8^3 -> 7^3 (offset 0)
 // 97 % of the 58.6 MFLOP per code are the three 3^3 convolutions with 64 output
 // channels.  They run as implicit GEMMs on tcgen05: activations live in HBM as
-// fp16 [B][6][6][6][C] (4^3 cube + zero halo), so that for every filter tap the
-// A operand of two codes (128 output positions x 64 channels) is ONE TMA box
-// {64,4,4,4,2} shifted by the tap; weights are [tap][cin/64][64 cout][64 cin] fp16.
+// fp16 [B][4][4][4][C]; for every filter tap the A operand of two codes (128
+// output positions x 64 channels) is ONE TMA box {64,4,4,4,2} whose start is
+// shifted by the tap - the TMA unit zero-fills what falls outside the 4^3 cube,
+// which IS the 'same' padding.  Weights are [tap][cin/64][cout][64 cin] fp16.
+// The last up-sampling layer (nearest x2 + 3^3 conv 64->1) is folded into the
+// same kernel: each of the 8 output parities is a conv over the 4^3 input with
+// pre-summed taps, i.e. a GEMM with N = 8 (padded to 16).
 // Per k-block (tap, cin chunk): TMA -> 128B-swizzled smem ring -> 4 x tcgen05.mma
 // (M128 N64 K16, fp32 accumulator in TMEM) issued by one thread; the epilogue
 // warps read TMEM (tcgen05.ld), add bias, ReLU, and store fp16 into the interior
@@ -114,43 +118,54 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
 
 // ---------------------------------------------------------------------------
 // from_code (1x1x1 conv 22->128 + ReLU) fused with the nearest x2 up-sampling:
-// writes the interior of act [B][6][6][6][128] fp16 (halo pre-zeroed).
+// writes act [B][4^3][128] fp16.  One block per code.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 dec_from_code_kernel(const float* __restrict__ codes, int64_t B, const float* __restrict__ w,
                      const float* __restrict__ bias, __half* __restrict__ act)
 {
-    // block = one code x one target position (4^3), thread = output channel
-    const int64_t b = blockIdx.x / 64;
-    const int pos = blockIdx.x % 64, z = pos >> 4, y = (pos >> 2) & 3, x = pos & 3;
-    const int src = ((z >> 1) * 2 + (y >> 1)) * 2 + (x >> 1);     // 2^3 source position
-    __shared__ float s_code[DEC_CF];
-    if (threadIdx.x < DEC_CF) s_code[threadIdx.x] = codes[b * (DEC_CF * 8) + threadIdx.x * 8 + src];
+    const int64_t b = blockIdx.x;
+    __shared__ float s_code[DEC_CF * 8];
+    __shared__ __half s_out[8][DEC_C1];
+    for (int i = threadIdx.x; i < DEC_CF * 8; i += 256) s_code[i] = codes[b * (DEC_CF * 8) + i];
     __syncthreads();
-    const int co = threadIdx.x;
-    float acc = bias[co];
+    for (int o = threadIdx.x; o < 8 * DEC_C1; o += 256) {
+        const int src = o / DEC_C1, co = o % DEC_C1;
+        float acc = bias[co];
 #pragma unroll
-    for (int ci = 0; ci < DEC_CF; ci++) acc = fmaf(w[co * DEC_CF + ci], s_code[ci], acc);
-    acc = fmaxf(acc, 0.0f);
-    act[(((b * 6 + z + 1) * 6 + y + 1) * 6 + x + 1) * DEC_C1 + co] = __float2half_rn(acc);
+        for (int ci = 0; ci < DEC_CF; ci++) acc = fmaf(w[co * DEC_CF + ci], s_code[ci * 8 + src], acc);
+        s_out[src][co] = __float2half_rn(fmaxf(acc, 0.0f));
+    }
+    __syncthreads();
+    // 64 target positions x 128 channels, 16 bytes per thread-iteration
+    uint4* dst = reinterpret_cast<uint4*>(act + b * 64 * DEC_C1);
+    for (int i = threadIdx.x; i < 64 * DEC_C1 / 8; i += 256) {
+        const int pos = i / (DEC_C1 / 8), c8 = i % (DEC_C1 / 8);
+        const int z = pos >> 4, y = (pos >> 2) & 3, x = pos & 3;
+        const int src = ((z >> 1) * 2 + (y >> 1)) * 2 + (x >> 1);
+        dst[i] = reinterpret_cast<const uint4*>(&s_out[src][0])[c8];
+    }
 }
 
 // ---------------------------------------------------------------------------
-// 3^3 convolution CIN -> 64 (+bias, ReLU) as an implicit GEMM on tcgen05.
+// 3^3 convolution CIN -> COUT (+bias, ReLU) as an implicit GEMM on tcgen05.
 // CTA = two codes (M = 128 output positions).  Warp 0: TMA producer, warp 1:
 // TMEM allocation + MMA issue, warps 2-5: epilogue (one TMEM lane quarter each).
+// COUT = 64: fp16 output [B][4^3][64].  COUT = 16: the folded up-sampling layer,
+// f32 output [B][8^3] (column = output parity, only 8 of the 16 are real).
 // ---------------------------------------------------------------------------
-template <int CIN>
+template <int CIN, int COUT>
 __global__ void __launch_bounds__(192, 1)
 dec_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
-                   const float* __restrict__ bias, __half* __restrict__ out, int64_t B)
+                   const float* __restrict__ bias, void* __restrict__ out_, int64_t B)
 {
     constexpr int NKB = 27 * (CIN / 64);
+    constexpr int W_BYTES = COUT * 128;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 128-byte swizzled tiles need 1024-byte alignment (the launch adds 1 KB of slack)
     unsigned char* sbase = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = sbase;                                      // [STAGES][16 KB]
-    unsigned char* sW = sbase + DEC_STAGES * DEC_A_BYTES;           // [STAGES][8 KB]
+    unsigned char* sW = sbase + DEC_STAGES * DEC_A_BYTES;           // [STAGES][COUT x 128 B]
     __shared__ __align__(8) uint64_t s_full[DEC_STAGES], s_empty[DEC_STAGES], s_acc;
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -178,21 +193,23 @@ dec_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_cons
                 if (it > 0) d_mbar_wait(&s_empty[s], (it - 1) & 1);
                 const int tap = kb / (CIN / 64), cc = kb % (CIN / 64);
                 const int dz = tap / 9, dy = (tap / 3) % 3, dx = tap % 3;
-                d_mbar_expect_tx(&s_full[s], DEC_A_BYTES + DEC_W_BYTES);
-                tma_load_5d(sA + s * DEC_A_BYTES, &tm_act, &s_full[s], cc * 64, dx, dy, dz, b0);
-                tma_load_2d(sW + s * DEC_W_BYTES, &tm_w, &s_full[s], 0, kb * 64);
+                d_mbar_expect_tx(&s_full[s], DEC_A_BYTES + W_BYTES);
+                // box start shifted by the tap; outside [0,4) the TMA unit writes zeros
+                tma_load_5d(sA + s * DEC_A_BYTES, &tm_act, &s_full[s], cc * 64, dx - 1, dy - 1,
+                            dz - 1, b0);
+                tma_load_2d(sW + s * W_BYTES, &tm_w, &s_full[s], 0, kb * COUT);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // instruction descriptor: D=F32, A=B=F16, both K-major, N=64, M=128
-            const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((64u >> 3) << 17) |
-                                   ((128u >> 4) << 24);
+            // instruction descriptor: D=F32, A=B=F16, both K-major, N=COUT, M=128
+            const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) |
+                                   (((uint32_t)COUT >> 3) << 17) | ((128u >> 4) << 24);
             for (int kb = 0; kb < NKB; kb++) {
                 const int s = kb % DEC_STAGES, it = kb / DEC_STAGES;
                 d_mbar_wait(&s_full[s], it & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint32_t a0 = smem_u32(sA + s * DEC_A_BYTES), w0 = smem_u32(sW + s * DEC_W_BYTES);
+                const uint32_t a0 = smem_u32(sA + s * DEC_A_BYTES), w0 = smem_u32(sW + s * W_BYTES);
 #pragma unroll
                 for (int k = 0; k < 4; k++)                           // 4 x K16 = 64 channels
                     umma_f16(tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(w0 + k * 32), idesc,
@@ -207,28 +224,43 @@ dec_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_cons
         const int m = q * 32 + lane;                                  // output row = (code, position)
         d_mbar_wait(&s_acc, 0);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        uint32_t r0[32], r1[32];
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-        TMEM_LD_32(taddr, r0);
-        TMEM_LD_32(taddr + 32, r1);
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
         const int64_t b = b0 + (m >> 6);
-        if (b < B) {
-            const int pos = m & 63, z = pos >> 4, y = (pos >> 2) & 3, x = pos & 3;
-            __half* dst = out + (((b * 6 + z + 1) * 6 + y + 1) * 6 + x + 1) * DEC_C0;
-            uint4 pk[8];
-            __half2* h2 = reinterpret_cast<__half2*>(pk);
+        const int pos = m & 63, z = pos >> 4, y = (pos >> 2) & 3, x = pos & 3;
+        if constexpr (COUT == 64) {
+            uint32_t r0[32], r1[32];
+            TMEM_LD_32(taddr, r0);
+            TMEM_LD_32(taddr + 32, r1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            if (b < B) {
+                __half* dst = reinterpret_cast<__half*>(out_) + (b * 64 + pos) * DEC_C0;
+                uint4 pk[8];
+                __half2* h2 = reinterpret_cast<__half2*>(pk);
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-                float v0 = fmaxf(__uint_as_float(r0[c]) + bias[c], 0.0f);
-                float v1 = fmaxf(__uint_as_float(r0[c + 1]) + bias[c + 1], 0.0f);
-                h2[c >> 1] = __floats2half2_rn(v0, v1);
-                float u0 = fmaxf(__uint_as_float(r1[c]) + bias[32 + c], 0.0f);
-                float u1 = fmaxf(__uint_as_float(r1[c + 1]) + bias[32 + c + 1], 0.0f);
-                h2[16 + (c >> 1)] = __floats2half2_rn(u0, u1);
+                for (int c = 0; c < 32; c += 2) {
+                    float v0 = fmaxf(__uint_as_float(r0[c]) + bias[c], 0.0f);
+                    float v1 = fmaxf(__uint_as_float(r0[c + 1]) + bias[c + 1], 0.0f);
+                    h2[c >> 1] = __floats2half2_rn(v0, v1);
+                    float u0 = fmaxf(__uint_as_float(r1[c]) + bias[32 + c], 0.0f);
+                    float u1 = fmaxf(__uint_as_float(r1[c + 1]) + bias[32 + c + 1], 0.0f);
+                    h2[16 + (c >> 1)] = __floats2half2_rn(u0, u1);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) reinterpret_cast<uint4*>(dst)[i] = pk[i];
             }
+        } else {
+            // folded up-sampling layer: column p = output parity (a,b,c) of position (z,y,x)
+            uint32_t r0[32];
+            TMEM_LD_32(taddr, r0);          // only the first 16 columns were written
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            if (b < B) {
+                float* dst = reinterpret_cast<float*>(out_) + b * 512;
 #pragma unroll
-            for (int i = 0; i < 8; i++) reinterpret_cast<uint4*>(dst)[i] = pk[i];
+                for (int p = 0; p < 8; p++) {
+                    const int oz = 2 * z + (p >> 2), oy = 2 * y + ((p >> 1) & 1), ox = 2 * x + (p & 1);
+                    dst[(oz * 8 + oy) * 8 + ox] = fmaxf(__uint_as_float(r0[p]) + bias[0], 0.0f);
+                }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -239,50 +271,28 @@ dec_conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------
-// tail: nearest x2 + 3^3 conv 64->1 + ReLU, two 3^3 convs 1->1, crop to 7^3.
-// One CTA per code, everything in shared memory (3 % of the flops, SIMT).
-// act: interior of [B][6][6][6][64] fp16; out: f32 [B][343] (logits, or
-// probabilities with apply_sigmoid).
+// tail: two 3^3 convs 1->1 (no activation) on the 8^3 map, crop to 7^3.
+// u: f32 [B][8^3]; out: f32 [B][343] (logits, or probabilities with
+// apply_sigmoid).  One warp-sized CTA group per code, SIMT (0.1 % of the flops).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-dec_tail_kernel(const __half* __restrict__ act, const float* __restrict__ w_up1,
-                const float* __restrict__ b_up1, const float* __restrict__ w_a,
+dec_tail_kernel(const float* __restrict__ u, const float* __restrict__ w_a,
                 const float* __restrict__ b_a, const float* __restrict__ w_b,
                 const float* __restrict__ b_b, int apply_sigmoid, float* __restrict__ out)
 {
-    __shared__ float s_in[64][65];          // [pos 4^3][channel], padded
-    __shared__ float s_w[27][64];
     __shared__ float s_u[10][10][10];       // 8^3 + zero halo
     __shared__ float s_v[10][10][10];
     const int64_t b = blockIdx.x;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 64 * 64; i += 256) {
-        int pos = i >> 6, c = i & 63, z = pos >> 4, y = (pos >> 2) & 3, x = pos & 3;
-        s_in[pos][c] = __half2float(act[(((b * 6 + z + 1) * 6 + y + 1) * 6 + x + 1) * DEC_C0 + c]);
-    }
-    for (int i = tid; i < 27 * 64; i += 256) s_w[i / 64][i % 64] = w_up1[(i % 64) * 27 + i / 64];
     for (int i = tid; i < 1000; i += 256) { (&s_u[0][0][0])[i] = 0.0f; (&s_v[0][0][0])[i] = 0.0f; }
     __syncthreads();
-    // up1: output 8^3; the up-sampled input at (z,y,x) is s_in[(z>>1, y>>1, x>>1)]
-    for (int o = tid; o < 512; o += 256) {
-        const int z = o >> 6, y = (o >> 3) & 7, x = o & 7;
-        float acc = b_up1[0];
-        for (int t = 0; t < 27; t++) {
-            const int zz = z + t / 9 - 1, yy = y + (t / 3) % 3 - 1, xx = x + t % 3 - 1;
-            if (zz < 0 || zz > 7 || yy < 0 || yy > 7 || xx < 0 || xx > 7) continue;
-            const float* a = s_in[((zz >> 1) * 4 + (yy >> 1)) * 4 + (xx >> 1)];
-            const float* wt = s_w[t];
-            float p = 0.0f;
-#pragma unroll 16
-            for (int c = 0; c < 64; c++) p = fmaf(a[c], wt[c], p);
-            acc += p;
-        }
-        s_u[z + 1][y + 1][x + 1] = fmaxf(acc, 0.0f);
-    }
+    for (int o = tid; o < 512; o += 256)
+        s_u[(o >> 6) + 1][((o >> 3) & 7) + 1][(o & 7) + 1] = u[b * 512 + o];
     __syncthreads();
     for (int o = tid; o < 512; o += 256) {
         const int z = o >> 6, y = (o >> 3) & 7, x = o & 7;
         float acc = b_a[0];
+#pragma unroll
         for (int t = 0; t < 27; t++)
             acc = fmaf(w_a[t], s_u[z + t / 9][y + (t / 3) % 3][x + t % 3], acc);
         s_v[z + 1][y + 1][x + 1] = acc;
@@ -291,6 +301,7 @@ dec_tail_kernel(const __half* __restrict__ act, const float* __restrict__ w_up1,
     for (int o = tid; o < 343; o += 256) {
         const int z = o / 49, y = (o / 7) % 7, x = o % 7;
         float acc = b_b[0];
+#pragma unroll
         for (int t = 0; t < 27; t++)
             acc = fmaf(w_b[t], s_v[z + t / 9][y + (t / 3) % 3][x + t % 3], acc);
         if (apply_sigmoid) acc = 1.0f / (1.0f + __expf(-acc));
@@ -323,9 +334,9 @@ static int make_act_map(CUtensorMap* tm, const __half* act, int64_t B, int C)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return ppp_fail(-1, "ppp_decode: cuTensorMapEncodeTiled unavailable");
-    cuuint64_t dims[5] = {(cuuint64_t)C, 6, 6, 6, (cuuint64_t)B};
-    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 12, (cuuint64_t)C * 72,
-                             (cuuint64_t)C * 432};
+    cuuint64_t dims[5] = {(cuuint64_t)C, 4, 4, 4, (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 8, (cuuint64_t)C * 32,
+                             (cuuint64_t)C * 128};
     cuuint32_t box[5] = {64, 4, 4, 4, 2};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)act, dims, strides, box, es,
@@ -334,13 +345,13 @@ static int make_act_map(CUtensorMap* tm, const __half* act, int64_t B, int C)
     return r == CUDA_SUCCESS ? 0 : ppp_fail(-1, "ppp_decode: activation tensor map failed");
 }
 
-static int make_w_map(CUtensorMap* tm, const __half* w, int nkb)
+static int make_w_map(CUtensorMap* tm, const __half* w, int nkb, int cout)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return ppp_fail(-1, "ppp_decode: cuTensorMapEncodeTiled unavailable");
-    cuuint64_t dims[2] = {64, (cuuint64_t)nkb * 64};
+    cuuint64_t dims[2] = {64, (cuuint64_t)nkb * cout};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, 64};
+    cuuint32_t box[2] = {64, (cuuint32_t)cout};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)w, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -350,44 +361,48 @@ static int make_w_map(CUtensorMap* tm, const __half* w, int nkb)
 
 extern "C" int64_t ppp_decode_scratch_bytes(int64_t B)
 {
-    // act0 [B][216][128] fp16 + two ping-pong [B][216][64] fp16
-    return B * 216 * (128 + 64 + 64) * 2 + 1024;
+    // act0 [B][64][128] fp16, two ping-pong [B][64][64] fp16, u f32 [B][512]
+    return B * 64 * (128 + 64 + 64) * 2 + B * 512 * 4 + 1024;
 }
 
 // weights (device): w_fc f32 [128][22], b_fc f32 [128];
 //   w_up0 fp16 [27][2][64][64], w_c0a / w_c0b fp16 [27][1][64][64]  ([tap][cin chunk][cout][cin]);
-//   b_up0, b_c0a, b_c0b f32 [64]; w_up1 f32 [64][27] (+b), w_c1a, w_c1b f32 [27] (+b).
+//   b_up0, b_c0a, b_c0b f32 [64];
+//   w_up1 fp16 [27][1][16][64]: the folded up-sampling layer, row p < 8 = output parity,
+//   rows 8..15 zero (b_up1 f32 [1]); w_c1a, w_c1b f32 [27] (+ scalar biases).
 extern "C" int ppp_decode(const float* codes, int64_t B, const float* w_fc, const float* b_fc,
                           const void* w_up0, const float* b_up0, const void* w_c0a,
                           const float* b_c0a, const void* w_c0b, const float* b_c0b,
-                          const float* w_up1, const float* b_up1, const float* w_c1a,
+                          const void* w_up1, const float* b_up1, const float* w_c1a,
                           const float* b_c1a, const float* w_c1b, const float* b_c1b,
                           int32_t apply_sigmoid, float* patches, void* scratch, void* stream)
 {
     if (B <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     __half* act0 = (__half*)scratch;
-    __half* act1 = act0 + B * 216 * 128;
-    __half* act2 = act1 + B * 216 * 64;
-    cudaMemsetAsync(scratch, 0, (size_t)B * 216 * (128 + 64 + 64) * 2, s);   // zero halos
-    dec_from_code_kernel<<<(unsigned)(B * 64), 128, 0, s>>>(codes, B, w_fc, b_fc, act0);
-    CUtensorMap ta0, ta1, ta2, tw0, tw1, tw2;
+    __half* act1 = act0 + B * 64 * 128;
+    __half* act2 = act1 + B * 64 * 64;
+    float* u = (float*)(act2 + B * 64 * 64);
+    dec_from_code_kernel<<<(unsigned)B, 256, 0, s>>>(codes, B, w_fc, b_fc, act0);
+    CUtensorMap ta0, ta1, ta2, tw0, tw1, tw2, tw3;
     int rc;
     if ((rc = make_act_map(&ta0, act0, B, 128))) return rc;
     if ((rc = make_act_map(&ta1, act1, B, 64))) return rc;
     if ((rc = make_act_map(&ta2, act2, B, 64))) return rc;
-    if ((rc = make_w_map(&tw0, (const __half*)w_up0, 54))) return rc;
-    if ((rc = make_w_map(&tw1, (const __half*)w_c0a, 27))) return rc;
-    if ((rc = make_w_map(&tw2, (const __half*)w_c0b, 27))) return rc;
+    if ((rc = make_w_map(&tw0, (const __half*)w_up0, 54, 64))) return rc;
+    if ((rc = make_w_map(&tw1, (const __half*)w_c0a, 27, 64))) return rc;
+    if ((rc = make_w_map(&tw2, (const __half*)w_c0b, 27, 64))) return rc;
+    if ((rc = make_w_map(&tw3, (const __half*)w_up1, 27, 16))) return rc;
     const size_t smem = DEC_STAGES * (DEC_A_BYTES + DEC_W_BYTES) + 1024;
-    cudaFuncSetAttribute(dec_conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(dec_conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(dec_conv_tc_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(dec_conv_tc_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(dec_conv_tc_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned grid = (unsigned)((B + 1) / 2);
-    dec_conv_tc_kernel<128><<<grid, 192, smem, s>>>(ta0, tw0, b_up0, act1, B);
-    dec_conv_tc_kernel<64><<<grid, 192, smem, s>>>(ta1, tw1, b_c0a, act2, B);
-    // act1's interior is fully overwritten by the third convolution, its halo is still zero
-    dec_conv_tc_kernel<64><<<grid, 192, smem, s>>>(ta2, tw2, b_c0b, act1, B);
-    dec_tail_kernel<<<(unsigned)B, 256, 0, s>>>(act1, w_up1, b_up1, w_c1a, b_c1a, w_c1b, b_c1b,
-                                                 apply_sigmoid, patches);
+    dec_conv_tc_kernel<128, 64><<<grid, 192, smem, s>>>(ta0, tw0, b_up0, act1, B);
+    dec_conv_tc_kernel<64, 64><<<grid, 192, smem, s>>>(ta1, tw1, b_c0a, act2, B);
+    dec_conv_tc_kernel<64, 64><<<grid, 192, smem, s>>>(ta2, tw2, b_c0b, act1, B);
+    dec_conv_tc_kernel<64, 16><<<grid, 192, smem, s>>>(ta1, tw3, b_up1, u, B);
+    dec_tail_kernel<<<(unsigned)B, 256, 0, s>>>(u, w_c1a, b_c1a, w_c1b, b_c1b, apply_sigmoid,
+                                                 patches);
     return ppp_check("ppp_decode");
 }

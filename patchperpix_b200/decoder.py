@@ -24,6 +24,24 @@ def _pack_conv(w):
     return np.ascontiguousarray(t.transpose(3, 1, 0, 2)).astype(np.float16)
 
 
+def _fold_upsample_conv(w):
+    """nearest x2 up-sampling followed by a 3^3 'same' convolution (weights
+    [1][64][3][3][3]) = for each output parity (a,b,c) a convolution over the
+    low-resolution input whose taps are sums of the original ones: along one
+    axis, parity 0 reads {i-1: w0, i: w1+w2}, parity 1 reads {i: w0+w1, i+1: w2}.
+    Returns fp16 [27][1][16][64] = [tap][cin chunk][parity (8 real, 8 zero)][cin]."""
+    w = np.asarray(w, np.float64)[0]                 # [64][3][3][3]
+    m = np.zeros((2, 3, 3))                          # [parity][low-res tap][original tap]
+    m[0, 0, 0] = 1; m[0, 1, 1] = 1; m[0, 1, 2] = 1
+    m[1, 1, 0] = 1; m[1, 1, 1] = 1; m[1, 2, 2] = 1
+    out = np.zeros((27, 1, 16, 64), np.float64)
+    for p in range(8):
+        a, b, c = p >> 2, (p >> 1) & 1, p & 1
+        f = np.einsum('cxyz,ix,jy,kz->ijkc', w, m[a], m[b], m[c])   # [3][3][3][64]
+        out[:, 0, p, :] = f.reshape(27, 64)
+    return out.astype(np.float16)
+
+
 class PatchDecoder:
     """weights: dict with the keys of oracle.decoder_torch.make_weights /
     the decoder part of the reference checkpoint (`model.decoder`)."""
@@ -43,7 +61,7 @@ class PatchDecoder:
         self.b_c0a = f(W['conv0a.b'])
         self.w_c0b = f(_pack_conv(W['conv0b.w']))
         self.b_c0b = f(W['conv0b.b'])
-        self.w_up1 = f(W['up1.w'].reshape(64, 27))
+        self.w_up1 = f(_fold_upsample_conv(W['up1.w']))
         self.b_up1 = f(W['up1.b'].reshape(1))
         self.w_c1a = f(W['conv1a.w'].reshape(27))
         self.b_c1a = f(W['conv1a.b'].reshape(1))
