@@ -190,8 +190,8 @@ __global__ void __launch_bounds__(RR_WARPS * 32)
 rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
                 const int32_t* __restrict__ rowvox, const float* __restrict__ cons,
                 const uint16_t* __restrict__ lists, const uint16_t* __restrict__ hlists,
-                const int32_t* __restrict__ meta, int64_t F, ppp_cfg cfg,
-                float* __restrict__ score)
+                const int32_t* __restrict__ meta, const uint32_t* __restrict__ perm, int64_t F,
+                ppp_cfg cfg, float* __restrict__ score)
 {
     Geo g = make_geo(cfg);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -212,8 +212,11 @@ rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ f
 
     for (int64_t grp = (int64_t)blockIdx.x * RR_WARPS + w; grp < ngroups;
          grp += (int64_t)gridDim.x * RR_WARPS) {
-        // lane s < RR_CPW owns centre row grp*RR_CPW + s
-        const int64_t myrow = grp * RR_CPW + lane;
+        // lane s < RR_CPW owns the centre with the (grp*RR_CPW + s)-th largest work
+        // (perm: rows sorted by term count, so that the centres of a warp finish
+        // together and the heavy warps start first)
+        const int64_t slot = grp * RR_CPW + lane;
+        const int64_t myrow = (lane < RR_CPW && slot < F) ? (int64_t)perm[slot] : F;
         int n_s = -1, nH_s = 0, nG_s = 0, vc_s = 0;
         if (lane < RR_CPW && myrow < F) {
             n_s = meta[myrow * 4]; nH_s = meta[myrow * 4 + 1]; nG_s = meta[myrow * 4 + 2];
@@ -252,7 +255,8 @@ rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ f
                 ok_[u] = ((live >> u) & 1u) && tt < n - 1;
                 const int j = tt < i ? tt : tt + 1;
                 after_[u] = j > i;
-                ej_[u] = ok_[u] ? lists[(grp * RR_CPW + u) * g.P + j] : 0;
+                const int64_t row_u = __shfl_sync(0xffffffffu, myrow, u);
+                ej_[u] = ok_[u] ? lists[row_u * g.P + j] : 0;
             }
 #pragma unroll
             for (int u = 0; u < RR_CPW; u++) {
@@ -313,11 +317,32 @@ rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ f
     }
 }
 
+// sort key: number of float additions of a centre, descending
+__global__ void rank_work_kernel(const int32_t* __restrict__ meta, int64_t F,
+                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= F) return;
+    int n = meta[r * 4], nH = meta[r * 4 + 1];
+    uint32_t work = (n > 0 && nH > 0) ? (uint32_t)nH * (uint32_t)(n - 1) : 0u;
+    keys[r] = ~work;
+    vals[r] = (uint32_t)r;
+}
+
+static size_t work_sort_bytes(int64_t F)
+{
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs((void*)nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)F);
+    return tb;
+}
+
 extern "C" int64_t ppp_rank_scratch_bytes(const ppp_cfg* cfg, int64_t F)
 {
     Geo g = make_geo(*cfg);
     if (F < 1) F = 1;
-    return 2 * ((F * g.P * 2 + 255) / 256) * 256 + ((F * 16 + 255) / 256) * 256 + 256;
+    return 2 * ((F * g.P * 2 + 255) / 256) * 256 + ((F * 16 + 255) / 256) * 256 +
+           4 * ((F * 4 + 255) / 256) * 256 + ((work_sort_bytes(F) + 255) / 256) * 256 + 256;
 }
 
 extern "C" int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fgidx,
@@ -341,8 +366,17 @@ extern "C" int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fg
     uint16_t* lists = (uint16_t*)scratch;
     uint16_t* hlists = (uint16_t*)((char*)scratch + lb);
     int32_t* meta = (int32_t*)((char*)scratch + 2 * lb);
+    size_t mb = ((F * 16 + 255) / 256) * 256, fb = ((F * 4 + 255) / 256) * 256;
+    uint32_t* keys = (uint32_t*)((char*)scratch + 2 * lb + mb);
+    uint32_t* keys_out = keys + fb / 4;
+    uint32_t* vals = keys_out + fb / 4;
+    uint32_t* perm = vals + fb / 4;
+    void* sort_tmp = (char*)scratch + 2 * lb + mb + 4 * fb;
+    size_t stb = work_sort_bytes(F);
     rank_lists_kernel<<<(unsigned)((F + 3) / 4), 128, 0, s>>>(dp, flags, rowvox, F, *cfg, lists,
                                                               hlists, meta);
+    rank_work_kernel<<<(unsigned)((F + 255) / 256), 256, 0, s>>>(meta, F, keys, vals);
+    cub::DeviceRadixSort::SortPairs(sort_tmp, stb, keys, keys_out, vals, perm, (int)F, 0, 32, s);
     size_t smem = (size_t)g.P * 4 + (size_t)(g.P + 1) * 2 + (size_t)RR_WARPS * RR_CPW * 33 * 4 + 32;
     cudaError_t e = cudaFuncSetAttribute(rank_ref_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -350,7 +384,7 @@ extern "C" int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fg
     int64_t ngroups = (F + RR_CPW - 1) / RR_CPW;
     int64_t nblk = (ngroups + RR_WARPS - 1) / RR_WARPS;
     rank_ref_kernel<<<(unsigned)nblk, RR_WARPS * 32, smem, s>>>(flags, fgidx, rowvox, cons, lists,
-                                                               hlists, meta, F, *cfg, score);
+                                                               hlists, meta, perm, F, *cfg, score);
     return ppp_check("ppp_rank(reference order)");
 }
 
