@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128)
 rank_lists_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
                   const int32_t* __restrict__ rowvox, int64_t F, ppp_cfg cfg,
                   uint16_t* __restrict__ lists, uint16_t* __restrict__ hlists,
-                  int32_t* __restrict__ meta)
+                  uint16_t* __restrict__ llists, int32_t* __restrict__ meta)
 {
     Geo g = make_geo(cfg);
     const int lane = threadIdx.x & 31;
@@ -174,6 +174,7 @@ rank_lists_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flag
                 int idx = n + __popc(bal & lt);
                 lists[row * g.P + idx] = (uint16_t)(po | (d > 0.0f ? 0x8000 : 0));
                 if (d > 0.0f) hlists[row * g.P + nH + __popc(balh & lt)] = (uint16_t)idx;
+                else llists[row * g.P + (n - nH) + __popc((bal & ~balh) & lt)] = (uint16_t)po;
             }
             n += __popc(bal);
             nH += __popc(balh);
@@ -186,16 +187,31 @@ rank_lists_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flag
 #define RR_WARPS 4
 #define RR_CPW 4
 
+// what every lane needs to know about the current high row of one centre
+struct __align__(16) RankRow {
+    const float* cbase;     // cons + row(p1)*K - lin(p1) - 1 : slot of (p1, p2) = cbase[lin(p2)]
+    int64_t loff;           // row * P: offset of this centre in lists / llists
+    int i;                  // list index of the high pixel p1
+    int t0;                 // first term of this round
+    int lb;                 // background entries before p1 (reversed terms come first)
+    int nslots;             // lb + (n - 1 - i)
+    int li;                 // lin(p1)
+    int vc;                 // centre voxel
+    int pad0, pad1;
+};
+
 __global__ void __launch_bounds__(RR_WARPS * 32)
 rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
                 const int32_t* __restrict__ rowvox, const float* __restrict__ cons,
                 const uint16_t* __restrict__ lists, const uint16_t* __restrict__ hlists,
-                const int32_t* __restrict__ meta, const uint32_t* __restrict__ perm, int64_t F,
-                ppp_cfg cfg, float* __restrict__ score)
+                const uint16_t* __restrict__ llists, const int32_t* __restrict__ meta,
+                const uint32_t* __restrict__ perm, int64_t F, ppp_cfg cfg,
+                float* __restrict__ score)
 {
     Geo g = make_geo(cfg);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int32_t* tab_dv = (int32_t*)smem_raw;                       // [P] voxel delta of patch pixel
+    RankRow* s_rows = (RankRow*)smem_raw;                       // [RR_WARPS][RR_CPW]
+    int32_t* tab_dv = (int32_t*)(s_rows + RR_WARPS * RR_CPW);   // [P] voxel delta of patch pixel
     uint16_t* tab_lin = (uint16_t*)(tab_dv + g.P);              // [P] position in the offset raster
     float* stage = (float*)(tab_lin + g.P + (g.P & 1));         // [RR_WARPS][RR_CPW][33]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -207,6 +223,7 @@ rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ f
     }
     __syncthreads();
     float* mystage = stage + w * RR_CPW * 33;
+    RankRow* myrows = s_rows + w * RR_CPW;
     const bool count_mode = (cfg.rank_flags & 2) != 0;
     const int64_t ngroups = (F + RR_CPW - 1) / RR_CPW;
 
@@ -223,68 +240,64 @@ rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ f
             vc_s = rowvox[myrow];
         }
         float acc = 0.0f;                 // running float sum of my centre
-        int cur_h = 0, cur_t = 0;         // current high row (index into hlist) and slot
-        int cur_i = 0, cur_li = 0;        // its list index and raster position
-        int64_t cur_row = 0;              // its consensus row base
+        int cur_h = 0;                    // current high row (index into hlist)
         bool alive = n_s > 0 && nH_s > 0;
-        if (alive) {
-            cur_i = hlists[myrow * g.P];
-            int ei = lists[myrow * g.P + cur_i] & 0x7fff;
-            cur_li = tab_lin[ei];
-            cur_row = (int64_t)fgidx[vc_s + tab_dv[ei]] * g.K;
-        }
+        auto open_row = [&]() {           // owner lane: publish high row cur_h
+            const int i = hlists[myrow * g.P + cur_h];
+            const int ei = lists[myrow * g.P + i] & 0x7fff;
+            const int li = tab_lin[ei];
+            RankRow r;
+            r.cbase = cons + (int64_t)fgidx[vc_s + tab_dv[ei]] * g.K - li - 1;
+            r.loff = myrow * g.P;
+            r.i = i; r.t0 = 0; r.lb = i - cur_h; r.nslots = (i - cur_h) + (n_s - 1 - i);
+            r.li = li; r.vc = vc_s; r.pad0 = 0; r.pad1 = 0;
+            myrows[lane] = r;
+        };
+        if (alive) open_row();
+        __syncwarp();
         while (true) {
             const unsigned live = __ballot_sync(0xffffffffu, alive);
             if (!live) break;
             // ---- gather 32 consecutive terms of every live centre, in three phases
             // (list entries, consensus values, hand-over) so that RR_CPW independent
             // loads are in flight per lane ---------------------------------------------
-            int after_[RR_CPW], li_[RR_CPW], ej_[RR_CPW], vc_[RR_CPW];
-            int64_t row_[RR_CPW];
-            bool ok_[RR_CPW];
+            int ej_[RR_CPW], li_[RR_CPW], vc_[RR_CPW];
+            const float* cb_[RR_CPW];
+            int st_[RR_CPW];                                     // 0 none, 1 after, 2 before
             float val_[RR_CPW];
 #pragma unroll
             for (int u = 0; u < RR_CPW; u++) {
-                const int i = __shfl_sync(0xffffffffu, cur_i, u);
-                const int t0 = __shfl_sync(0xffffffffu, cur_t, u);
-                const int n = __shfl_sync(0xffffffffu, n_s, u);
-                li_[u] = __shfl_sync(0xffffffffu, cur_li, u);
-                row_[u] = __shfl_sync(0xffffffffu, cur_row, u);
-                vc_[u] = __shfl_sync(0xffffffffu, vc_s, u);
-                const int tt = t0 + lane;
-                ok_[u] = ((live >> u) & 1u) && tt < n - 1;
-                const int j = tt < i ? tt : tt + 1;
-                after_[u] = j > i;
-                const int64_t row_u = __shfl_sync(0xffffffffu, myrow, u);
-                ej_[u] = ok_[u] ? lists[row_u * g.P + j] : 0;
+                const RankRow r = myrows[u];                     // broadcast
+                const int tt = r.t0 + lane;
+                const bool ok = ((live >> u) & 1u) && tt < r.nslots;
+                const bool before = tt < r.lb;
+                st_[u] = ok ? (before ? 2 : 1) : 0;
+                cb_[u] = r.cbase; li_[u] = r.li; vc_[u] = r.vc;
+                ej_[u] = !ok ? 0 : (before ? (int)llists[r.loff + tt]
+                                           : (int)lists[r.loff + r.i + 1 + (tt - r.lb)]);
             }
 #pragma unroll
             for (int u = 0; u < RR_CPW; u++) {
                 const int pj = ej_[u] & 0x7fff;
-                const bool hj = (ej_[u] & 0x8000) != 0;
                 const int lj = tab_lin[pj];
                 float v3 = 0.0f;
-                if (ok_[u]) {
-                    if (after_[u]) v3 = cons[row_[u] + lj - li_[u] - 1];
-                    else if (!hj)
-                        v3 = cons[(int64_t)fgidx[vc_[u] + tab_dv[pj]] * g.K + li_[u] - lj - 1];
-                }
+                if (st_[u] == 1) v3 = cb_[u][lj];
+                else if (st_[u] == 2)
+                    v3 = cons[(int64_t)fgidx[vc_[u] + tab_dv[pj]] * g.K + li_[u] - lj - 1];
                 val_[u] = v3;
             }
 #pragma unroll
             for (int u = 0; u < RR_CPW; u++) {
                 const bool hj = (ej_[u] & 0x8000) != 0;
                 float v3 = val_[u], val = 0.0f;
-                if (ok_[u]) {
-                    if (after_[u]) {
-                        // rankPatches.cu:88-100 (both high) / :102-137 (high, background)
-                        if (count_mode) v3 = (v3 != 0.0f) ? copysignf(1.0f, v3) : (hj ? -1.0f : 1.0f);
-                        val = hj ? v3 : -v3;
-                    } else if (!hj) {
-                        // background pixel before the high one: reversed slot (:109-126)
-                        if (count_mode) v3 = (v3 != 0.0f) ? copysignf(1.0f, v3) : 1.0f;
-                        val = -v3;
-                    }
+                if (st_[u] == 1) {
+                    // rankPatches.cu:88-100 (both high) / :102-137 (high, background)
+                    if (count_mode) v3 = (v3 != 0.0f) ? copysignf(1.0f, v3) : (hj ? -1.0f : 1.0f);
+                    val = hj ? v3 : -v3;
+                } else if (st_[u] == 2) {
+                    // background pixel before the high one: reversed slot (:109-126)
+                    if (count_mode) v3 = (v3 != 0.0f) ? copysignf(1.0f, v3) : 1.0f;
+                    val = -v3;
                 }
                 mystage[u * 33 + lane] = val;
             }
@@ -294,18 +307,12 @@ rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ f
                 const float* st = mystage + lane * 33;
 #pragma unroll
                 for (int q = 0; q < 32; q++) acc += st[q];
-                cur_t += 32;
-                if (cur_t >= n_s - 1) {                         // next high row
-                    cur_t = 0;
+                const int t1 = myrows[lane].t0 + 32;
+                if (t1 >= myrows[lane].nslots) {                 // next high row
                     cur_h++;
                     if (cur_h >= nH_s) alive = false;
-                    else {
-                        cur_i = hlists[myrow * g.P + cur_h];
-                        int ei = lists[myrow * g.P + cur_i] & 0x7fff;
-                        cur_li = tab_lin[ei];
-                        cur_row = (int64_t)fgidx[vc_s + tab_dv[ei]] * g.K;
-                    }
-                }
+                    else open_row();
+                } else myrows[lane].t0 = t1;
             }
             __syncwarp();
         }
@@ -324,7 +331,8 @@ __global__ void rank_work_kernel(const int32_t* __restrict__ meta, int64_t F,
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= F) return;
     int n = meta[r * 4], nH = meta[r * 4 + 1];
-    uint32_t work = (n > 0 && nH > 0) ? (uint32_t)nH * (uint32_t)(n - 1) : 0u;
+    uint32_t work = (n > 0 && nH > 0)
+        ? (uint32_t)nH * (uint32_t)(n - 1) - ((uint32_t)nH * (uint32_t)(nH - 1)) / 2 : 0u;
     keys[r] = ~work;
     vals[r] = (uint32_t)r;
 }
@@ -341,7 +349,7 @@ extern "C" int64_t ppp_rank_scratch_bytes(const ppp_cfg* cfg, int64_t F)
 {
     Geo g = make_geo(*cfg);
     if (F < 1) F = 1;
-    return 2 * ((F * g.P * 2 + 255) / 256) * 256 + ((F * 16 + 255) / 256) * 256 +
+    return 3 * ((F * g.P * 2 + 255) / 256) * 256 + ((F * 16 + 255) / 256) * 256 +
            4 * ((F * 4 + 255) / 256) * 256 + ((work_sort_bytes(F) + 255) / 256) * 256 + 256;
 }
 
@@ -365,26 +373,29 @@ extern "C" int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fg
     size_t lb = ((F * g.P * 2 + 255) / 256) * 256;
     uint16_t* lists = (uint16_t*)scratch;
     uint16_t* hlists = (uint16_t*)((char*)scratch + lb);
-    int32_t* meta = (int32_t*)((char*)scratch + 2 * lb);
+    uint16_t* llists = (uint16_t*)((char*)scratch + 2 * lb);
+    int32_t* meta = (int32_t*)((char*)scratch + 3 * lb);
     size_t mb = ((F * 16 + 255) / 256) * 256, fb = ((F * 4 + 255) / 256) * 256;
-    uint32_t* keys = (uint32_t*)((char*)scratch + 2 * lb + mb);
+    uint32_t* keys = (uint32_t*)((char*)scratch + 3 * lb + mb);
     uint32_t* keys_out = keys + fb / 4;
     uint32_t* vals = keys_out + fb / 4;
     uint32_t* perm = vals + fb / 4;
-    void* sort_tmp = (char*)scratch + 2 * lb + mb + 4 * fb;
+    void* sort_tmp = (char*)scratch + 3 * lb + mb + 4 * fb;
     size_t stb = work_sort_bytes(F);
     rank_lists_kernel<<<(unsigned)((F + 3) / 4), 128, 0, s>>>(dp, flags, rowvox, F, *cfg, lists,
-                                                              hlists, meta);
+                                                              hlists, llists, meta);
     rank_work_kernel<<<(unsigned)((F + 255) / 256), 256, 0, s>>>(meta, F, keys, vals);
     cub::DeviceRadixSort::SortPairs(sort_tmp, stb, keys, keys_out, vals, perm, (int)F, 0, 32, s);
-    size_t smem = (size_t)g.P * 4 + (size_t)(g.P + 1) * 2 + (size_t)RR_WARPS * RR_CPW * 33 * 4 + 32;
+    size_t smem = (size_t)RR_WARPS * RR_CPW * sizeof(RankRow) + (size_t)g.P * 4 +
+                  (size_t)(g.P + 1) * 2 + (size_t)RR_WARPS * RR_CPW * 33 * 4 + 32;
     cudaError_t e = cudaFuncSetAttribute(rank_ref_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return ppp_fail((int)e, "ppp_rank: smem attribute");
     int64_t ngroups = (F + RR_CPW - 1) / RR_CPW;
     int64_t nblk = (ngroups + RR_WARPS - 1) / RR_WARPS;
     rank_ref_kernel<<<(unsigned)nblk, RR_WARPS * 32, smem, s>>>(flags, fgidx, rowvox, cons, lists,
-                                                               hlists, meta, perm, F, *cfg, score);
+                                                               hlists, llists, meta, perm, F, *cfg,
+                                                               score);
     return ppp_check("ppp_rank(reference order)");
 }
 
