@@ -102,9 +102,11 @@ int ppp_prepare_patches(const float* pred, const uint8_t* flags,
 
 /* ---- step 1: consensus (fillConsensusArray.cu + normConsensusArray.cu) ----
  * cons f32 [F][K] (normalised iff cfg->norm_aff), cnt u32 [F][K].
- * impl: 0 = tiled (vote counters from `rbits`, sums from shared-memory tiles;
- * needs rbits and scratch of ppp_consensus_scratch_bytes(cfg)), 1 = the simple
- * one-CTA-per-voxel gather kept as a cross-check (rbits/scratch/cnt may be NULL). */
+ * impl: 0 = automatic: small patches (psx < 16) use the bit-guided gather (one
+ * kernel, visits only the centres that vote), larger ones the tiled pair of
+ * kernels (vote counters from `rbits`, sums from TMA-staged shared-memory tiles);
+ * 1 = the simple one-CTA-per-voxel gather kept as a cross-check (rbits, scratch
+ * and cnt may be NULL); 2 = force the bit-guided gather; 3 = force tiled. */
 int64_t ppp_consensus_scratch_bytes(const ppp_cfg* cfg);
 int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8_t* flags,
                   const int32_t* fgidx, const int32_t* rowvox, int64_t F,

@@ -145,6 +145,79 @@ consensus_count_kernel(const unsigned long long* __restrict__ rbits,
 }
 
 // ---------------------------------------------------------------------------
+// small patches (psx < 16, e.g. the 7^3 patches of the flylight setup on sparse
+// 3-D data): counters AND sums in one kernel, one thread per slot.  The
+// received class bits say exactly which centres vote for the slot, so the
+// thread only visits those (a handful on thin neurites) instead of the whole
+// window intersection; the slot is then written once, coalesced.  Centres are
+// visited in raster order: bit-identical to the simple kernel.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+consensus_bits_kernel(const float* __restrict__ dp, const unsigned long long* __restrict__ rbits,
+                      const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
+                      const int32_t* __restrict__ rowvox, int64_t F, ppp_cfg cfg,
+                      float* __restrict__ cons, uint32_t* __restrict__ cnt)
+{
+    Geo g = make_geo(cfg);
+    const int64_t row = blockIdx.x;
+    const int vb = rowvox[row];
+    int bz, by, bx;
+    vox_decode(g, vb, bz, by, bx);
+    const bool gated = (flags[vb] & PPP_FLAG_GATED) != 0;
+    const int nrw = g.psz * g.psy;
+    const unsigned long long* rb = rbits + row * nrw * 2;
+    for (int k = threadIdx.x; k < g.K; k += blockDim.x) {
+        float out = 0.0f;
+        uint32_t outc = 0;
+        int lin = k + g.K + 1;
+        int ox = lin % g.nx - (g.psx - 1);
+        int t = lin / g.nx;
+        int oy = t % g.ny - (g.psy - 1);
+        int oz = t / g.ny - (g.psz - 1);
+        int pz = bz + oz, py = by + oy, px = bx + ox;
+        if (gated && pz >= 0 && pz < g.Z && py >= 0 && py < g.Y && px >= 0 && px < g.X) {
+            int vp = (pz * g.Y + py) * g.X + px;
+            if (flags[vp] & PPP_FLAG_GATED) {
+                const unsigned long long* rp = rbits + (int64_t)fgidx[vp] * nrw * 2;
+                int pos = 0, neg = 0;
+                float sum = 0.0f;
+                int dz0 = max(-g.rz, oz - g.rz), dz1 = min(g.rz, oz + g.rz);
+                int dy0 = max(-g.ry, oy - g.ry), dy1 = min(g.ry, oy + g.ry);
+                for (int dz = dz0; dz <= dz1; dz++)
+                for (int dy = dy0; dy <= dy1; dy++) {
+                    int w1 = (dz + g.rz) * g.psy + (dy + g.ry);
+                    int w2 = (dz - oz + g.rz) * g.psy + (dy - oy + g.ry);
+                    unsigned long long h1 = rb[2 * w1], l1 = rb[2 * w1 + 1];
+                    unsigned long long h2 = rp[2 * w2], l2 = rp[2 * w2 + 1];
+                    if (ox >= 0) { h2 <<= ox; l2 <<= ox; } else { h2 >>= -ox; l2 >>= -ox; }
+                    pos += __popcll(h1 & h2);
+                    neg += __popcll(h1 & l2) + __popcll(l1 & h2);
+                    unsigned long long m = (h1 & (h2 | l2)) | (l1 & h2);   // centres that vote
+                    if (!m || cfg.prod_mode == 0) continue;
+                    const int64_t cline = ((int64_t)(bz + dz) * g.Y + (by + dy)) * g.X;
+                    // patch rows that talk about b and about b + o, seen from this centre line
+                    const int64_t pr1 = (int64_t)((g.rz - dz) * g.psy + (g.ry - dy)) * F;
+                    const int64_t pr2 = (int64_t)((g.rz - dz + oz) * g.psy + (g.ry - dy + oy)) * F;
+                    while (m) {
+                        int tb = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        int cx = bx - g.rx + tb;
+                        int64_t rc = fgidx[cline + cx];
+                        float d1 = dp[(pr1 + rc) * g.rsg + DP_GUARD + (bx - cx + g.rx)];
+                        float d2 = dp[(pr2 + rc) * g.rsg + DP_GUARD + (px - cx + g.rx)];
+                        sum = fmaf(d1, d2, sum);
+                    }
+                }
+                out = consensus_epilogue(cfg, sum, pos, neg);
+                outc = ((uint32_t)neg << 16) | (uint32_t)pos;
+            }
+        }
+        cons[row * g.K + k] = out;
+        cnt[row * g.K + k] = outc;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // sums.  CTA = (base line, group of NOY consecutive offset rows (oz,oy)).
 //
 // Rows of `dp` are in raster order, so the valid centres of a line are a
@@ -525,6 +598,11 @@ extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8
     if (g.X > CT_XMAX) return ppp_fail(-1, "ppp_consensus: X > 2048 unsupported, use blocks");
     if (g.psz * g.psy > CT_MAXLINES)
         return ppp_fail(-1, "ppp_consensus: more than 128 centre lines per window");
+    if (impl == 2 || (impl == 0 && g.psx < 16)) {
+        consensus_bits_kernel<<<(unsigned)F, 128, 0, s>>>(
+            dp, (const unsigned long long*)rbits, flags, fgidx, rowvox, F, *cfg, cons, cnt);
+        return ppp_check("ppp_consensus(bits)");
+    }
     consensus_count_kernel<<<(unsigned)F, 256, 0, s>>>(
         (const unsigned long long*)rbits, flags, fgidx, rowvox, *cfg, cons, cnt);
     if (cfg->prod_mode == 0) return ppp_check("ppp_consensus(count)");   // no float sums needed
