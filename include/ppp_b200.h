@@ -162,6 +162,19 @@ int64_t ppp_label_scratch_bytes(int64_t V, int64_t n);
 int ppp_label_cc(const uint32_t* pairs, const float* aff, int64_t n,
                  const ppp_cfg* cfg, int32_t* comp, int32_t* n_comp,
                  void* scratch, void* stream);
+/* mutex watershed instead of thresholded components -- the flylight default
+ * `mws = true` (graph_mws.py:7-85 on the graph of aff_patch_graph.py:31-40).
+ * HOST function, HOST pointers: one serial greedy pass over the edges sorted by
+ * |aff| (every decision depends on the earlier ones; a few thousand edges).
+ * node_vox / node_label i32 [<= 2n] out: voxel index and component id of every
+ * graph node in insertion order; id 0 = the node joined nothing and is not
+ * painted.  Ids equal the reference's instance values (merged-away ids leave
+ * gaps).  *n_nodes, *n_labels (= largest id) out.  Scatter node_label into
+ * comp[node_vox] and paint with ppp_paint / ppp_paint_patches. */
+int ppp_mws_host(const uint32_t* pairs, const float* aff, int64_t n,
+                 const ppp_cfg* cfg, int32_t* node_vox, int32_t* node_label,
+                 int64_t* n_nodes, int32_t* n_labels);
+
 /* instances i32 [V] (zeroed by the caller): for every node with comp > 0,
  * window pixels with pred > pt_gt take max(comp) ("later components overwrite
  * earlier ones", graph_to_labeling.py:84).  nodes[m] voxel indices. */

@@ -136,9 +136,54 @@ def patch_pairs(selected_list, patchshape, include_single=True, max_ps_dist=2):
     return arr
 
 
+def mutex_watershed(g):
+    """graph_mws.py:7-85 restated: greedy pass over the edges by decreasing
+    |aff|; an attractive edge joins two clusters unless a repulsive edge seen
+    earlier connects them.  Returns the reference's list of components (some
+    empty: ids of merged-away components stay in the numbering)."""
+    ids = {n: i for i, n in enumerate(g.nodes())}
+    names = list(g.nodes())
+    edges = []
+    for u, v, a in g.edges.data('aff'):
+        edges.append((ids[u], ids[v], a, True) if a > 0 else (ids[u], ids[v], -a, False))
+    edges.sort(key=lambda e: e[2], reverse=True)          # stable
+    comp = {i: 0 for i in ids.values()}                   # node -> component id, 0 = none
+    member = {0: set(ids.values())}                       # component id -> nodes
+    repulsive = []
+
+    def blocked(test):
+        return any(test(e, f) or test(f, e) for e, f in repulsive)
+
+    for u, v, _, attractive in edges:
+        if not attractive:
+            repulsive.append((u, v))
+            continue
+        cu, cv = comp[u], comp[v]
+        if cu == 0 and cv == 0:
+            new = max(comp.values()) + 1
+            member[new] = {u, v}
+            member[0] -= {u, v}
+            comp[u] = comp[v] = new
+        elif cu == 0 or cv == 0:
+            c = max(cu, cv)
+            lone = u if cu == 0 else v
+            if not blocked(lambda e, f: comp[e] == c and f == lone):
+                member[c] |= {u, v}
+                member[0] -= {u, v}
+                comp[u] = comp[v] = c
+        elif cu != cv:
+            if not blocked(lambda e, f: comp[e] == cu and comp[f] == cv):
+                keep, gone = min(cu, cv), max(cu, cv)
+                member[keep] = member[cu] | member[cv]
+                for e in member[gone]:
+                    comp[e] = keep
+                member[gone] = set()
+    return [[names[i] for i in member[c]] for c in member if c > 0]
+
+
 def label_instances(pairs, aff, pred, patchshape, rad, shape, patch_threshold,
-                    dtype=np.uint16):
-    """aff_patch_graph.py:31-40 + graph_to_labeling.py:50-84 (mws False)."""
+                    dtype=np.uint16, mws=False):
+    """aff_patch_graph.py:31-40 + graph_to_labeling.py:44-84."""
     g = nx.Graph()
     for i, a in enumerate(aff):
         if a != 0:
@@ -150,7 +195,8 @@ def label_instances(pairs, aff, pred, patchshape, rad, shape, patch_threshold,
             pos.add_edge(e0, e1, weight=a)
     inst = np.zeros(shape, dtype)
     comps = []
-    for k, cc in enumerate(nx.connected_components(pos)):
+    ccs = mutex_watershed(g) if mws else nx.connected_components(pos)
+    for k, cc in enumerate(ccs):
         comps.append(sorted(cc))
         for idx in cc:
             idx = np.array(idx)
@@ -192,7 +238,8 @@ def assemble(pred, foreground, numinst, patchshape, kw, kern):
     aff = kern.patch_graph(pairs)
     out['aff'] = aff
     inst, comps = label_instances(pairs, aff, pred, ps, rad, foreground.shape,
-                                  np.float32(kw['patch_threshold']))
+                                  np.float32(kw['patch_threshold']),
+                                  mws=kw.get('mws', False))
     out['instances'] = inst
     out['components'] = comps
     return out
@@ -232,6 +279,8 @@ def oracle_block_fn(block, foreground, mask, numinst, **kw):
                             kw.get('max_total_patch_distance_in_ps_multiples', 2))
     if pairs is None or len(pairs) == 0:
         return None, None
+    assert np.all(pairs.astype(np.int64) < np.tile(np.array(pred.shape[1:]), 2)), \
+        "pair centre outside the block (the reference would read out of bounds)"
     return pairs, O.patch_graph(pairs)
 
 
@@ -240,5 +289,6 @@ def oracle_paint_fn(inputs, pairs, aff, rank=0, world=1, **kw):
     ps = np.array(kw['patchshape'])
     pred = np.asarray(inputs.pred).astype(np.float32)
     inst, _ = label_instances(pairs, aff, pred, ps, ps // 2, inputs.shape,
-                              np.float32(kw['patch_threshold']), dtype=np.uint32)
+                              np.float32(kw['patch_threshold']), dtype=np.uint32,
+                              mws=kw.get('mws', False))
     return inst

@@ -19,6 +19,28 @@ def _torch():
     return torch
 
 
+def mutex_watershed(pairs, aff, cfg):
+    """graph_mws.mws on the graph of setAffgraph (graph_mws.py:7-85,
+    aff_patch_graph.py:31-40) through ppp_mws_host: the one serial graph pass of
+    the path, host side like the pair search.  pairs u32 [n,6], aff f32 [n]
+    (numpy); cfg carries the volume shape.  Returns (node_vox i32 [m],
+    node_label i32 [m], largest label); label 0 = node joined nothing."""
+    import ctypes
+    pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 6)
+    aff = np.ascontiguousarray(aff, np.float32)
+    n = len(aff)
+    assert len(pairs) == n
+    node_vox = np.zeros(max(1, 2 * n), np.int32)
+    node_label = np.zeros(max(1, 2 * n), np.int32)
+    n_nodes = ctypes.c_int64(0)
+    top = ctypes.c_int32(0)
+    cc.call('ppp_mws_host', pairs.ctypes.data, aff.ctypes.data, n, cfg,
+            node_vox.ctypes.data, node_label.ctypes.data,
+            ctypes.addressof(n_nodes), ctypes.addressof(top))
+    m = int(n_nodes.value)
+    return node_vox[:m].copy(), node_label[:m].copy(), int(top.value)
+
+
 class BlockAssembler:
     """state of one block on the device.
 
@@ -224,14 +246,26 @@ class BlockAssembler:
         return aff[:n]
 
     # -- step 6 ------------------------------------------------------------
-    def label(self, pairs_dev, aff, nodes, pred=None, cfg=None):
+    def label(self, pairs_dev, aff, nodes, pred=None, cfg=None, mws=False):
         """setAffgraph + affGraphToInstances (aff_patch_graph.py:31-40,
-        graph_to_labeling.py:50-84).  Returns (instances i32 [Z,Y,X], n_comp)."""
+        graph_to_labeling.py:44-84).  Returns (instances i32 [Z,Y,X], n_comp).
+        mws: partition by mutex watershed (graph_mws.py) instead of the
+        components over aff > 0."""
         torch = _torch()
         cfg = cfg or self.cfg
         pred = self.pred if pred is None else pred
         n = int(pairs_dev.shape[0])
         V = self.V
+        if mws:
+            node_vox, node_label, top = mutex_watershed(
+                pairs_dev.cpu().numpy(), aff.cpu().numpy(), cfg)
+            comp = torch.zeros(V, dtype=torch.int32, device=self.dev)
+            nodes = torch.from_numpy(node_vox).to(self.dev)
+            comp[nodes.long()] = torch.from_numpy(node_label).to(self.dev)
+            inst = torch.zeros(self.shape, dtype=torch.int32, device=self.dev)
+            cc.call('ppp_paint', cc.ptr(pred), cc.ptr(nodes), int(nodes.numel()), cc.ptr(comp),
+                    cfg, cc.ptr(inst), self.stream)
+            return inst, top
         comp = torch.empty(V, dtype=torch.int32, device=self.dev)
         ncomp = torch.zeros(1, dtype=torch.int32, device=self.dev)
         scratch = torch.empty(cc.call('ppp_label_scratch_bytes', V, n), dtype=torch.uint8,

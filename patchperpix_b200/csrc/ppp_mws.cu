@@ -1,0 +1,152 @@
+// Mutex-watershed partition of the patch graph -- the flylight default
+// (`mws = true`), reference: PatchPerPix/vote_instances/graph_mws.py:7-85 on the
+// graph that setAffgraph builds (aff_patch_graph.py:31-40).
+//
+// HOST code by design.  The algorithm is one greedy pass over the edges in
+// order of decreasing |aff| where every decision depends on all earlier ones;
+// the graph has a few thousand edges per block (and is what the blockwise
+// driver gathers on every rank anyway), so the pass costs well under a
+// millisecond on one core, less than a single dependent-load chain would on the
+// device.  Everything around it stays on the GPU: the affinities come from
+// ppp_patch_graph, the labels go to ppp_paint.
+//
+// What has to be reproduced exactly, because label VALUES depend on it:
+//  * edge order = networkx edge iteration (nodes in insertion order, neighbours
+//    in insertion order, each edge once), then a stable sort by |aff|, descending;
+//  * component ids: a new component takes max(id in use) + 1, a merge keeps the
+//    smaller id, ids of merged-away components are skipped in the numbering
+//    unless they were the maximum (then they are taken again);
+//  * nodes that never join through an accepted attractive edge get no label;
+//  * the mutex test is on clusters (a cluster-level restatement of the
+//    reference's scan over all mutex edges, same outcome).
+#include "../../include/ppp_b200.h"
+#include "ppp_api.cuh"
+
+#include <algorithm>
+#include <cstdint>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+namespace {
+
+struct MwsEdge { int u, v; float w; bool attractive; };
+
+struct Clusters {
+    std::vector<int> parent;
+    std::vector<std::unordered_set<int>> mutex;      // by root: roots it must not join
+    explicit Clusters(int n) : parent(n), mutex(n) { for (int i = 0; i < n; i++) parent[i] = i; }
+    int find(int a) {
+        while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; }
+        return a;
+    }
+    bool exclusive(int a, int b) const { return mutex[a].count(b) != 0; }
+    void forbid(int a, int b) { if (a != b) { mutex[a].insert(b); mutex[b].insert(a); } }
+    int join(int a, int b) {                          // returns the surviving root
+        if (a == b) return a;
+        if (mutex[a].size() < mutex[b].size()) std::swap(a, b);
+        parent[b] = a;
+        for (int c : mutex[b]) {
+            mutex[c].erase(b);
+            mutex[c].insert(a);
+            mutex[a].insert(c);
+        }
+        std::unordered_set<int>().swap(mutex[b]);
+        return a;
+    }
+};
+
+}  // namespace
+
+extern "C" int ppp_mws_host(const uint32_t* pairs, const float* aff, int64_t n,
+                            const ppp_cfg* cfg, int32_t* node_vox, int32_t* node_label,
+                            int64_t* n_nodes, int32_t* n_labels)
+{
+    if (!cfg || !n_nodes || !n_labels || (n > 0 && (!pairs || !aff || !node_vox || !node_label)))
+        return ppp_fail(-1, "ppp_mws_host: null argument");
+    const int64_t Y = cfg->Y, X = cfg->X;
+
+    // --- the graph, with networkx's iteration order --------------------------
+    std::unordered_map<int64_t, int> id_of;
+    std::vector<int64_t> vox;
+    std::vector<std::vector<std::pair<int, int>>> adj;   // (neighbour, edge slot)
+    std::unordered_map<uint64_t, int> slot_of;           // unordered node pair -> slot
+    std::vector<float> weight;
+    auto node = [&](const uint32_t* c) {
+        int64_t v = ((int64_t)c[0] * Y + c[1]) * X + c[2];
+        auto it = id_of.find(v);
+        if (it != id_of.end()) return it->second;
+        int id = (int)vox.size();
+        id_of.emplace(v, id);
+        vox.push_back(v);
+        adj.emplace_back();
+        return id;
+    };
+    for (int64_t i = 0; i < n; i++) {
+        if (aff[i] == 0.0f) continue;                     // aff_patch_graph.py:36
+        int u = node(pairs + 6 * i), v = node(pairs + 6 * i + 3);
+        uint64_t key = ((uint64_t)(uint32_t)std::min(u, v) << 32) | (uint32_t)std::max(u, v);
+        auto it = slot_of.find(key);
+        if (it != slot_of.end()) { weight[it->second] = aff[i]; continue; }   // attribute overwritten
+        int s = (int)weight.size();
+        slot_of.emplace(key, s);
+        weight.push_back(aff[i]);
+        adj[u].push_back({v, s});
+        if (v != u) adj[v].push_back({u, s});
+    }
+    const int nn = (int)vox.size();
+    std::vector<MwsEdge> edges;
+    edges.reserve(weight.size());
+    {
+        std::vector<char> seen(nn, 0);
+        for (int u = 0; u < nn; u++) {
+            for (auto& e : adj[u]) {
+                if (seen[e.first]) continue;
+                float a = weight[e.second];
+                edges.push_back({u, e.first, a > 0 ? a : -a, a > 0});   // graph_mws.py:22-26
+            }
+            seen[u] = 1;
+        }
+    }
+    std::stable_sort(edges.begin(), edges.end(),
+                     [](const MwsEdge& a, const MwsEdge& b) { return a.w > b.w; });  // :28
+
+    // --- the greedy pass (:33-75) --------------------------------------------
+    Clusters cl(nn);
+    std::vector<int> cid(nn, 0);          // by root: the reference's component id, 0 = none yet
+    std::vector<int> members(1, 0);       // by component id: nodes carrying it
+    int max_id = 0;                       // np.max(node_CCs.values())
+    for (const MwsEdge& e : edges) {
+        int a = cl.find(e.u), b = cl.find(e.v);
+        if (!e.attractive) { cl.forbid(a, b); continue; }
+        int ca = cid[a], cb = cid[b];
+        if (ca == 0 && cb == 0) {                         // :37-43 (no mutex test here)
+            int id = max_id + 1;
+            if ((int)members.size() <= id) members.resize(id + 1, 0);
+            members[id] = (e.u == e.v) ? 1 : 2;
+            cid[cl.join(a, b)] = id;
+            max_id = id;
+        } else if (ca == 0 || cb == 0) {                  // :45-57
+            if (cl.exclusive(a, b)) continue;
+            int id = std::max(ca, cb);
+            cid[cl.join(a, b)] = id;
+            members[id] += 1;
+        } else if (ca != cb) {                            // :58-73
+            if (cl.exclusive(a, b)) continue;
+            int keep = std::min(ca, cb), gone = std::max(ca, cb);
+            cid[cl.join(a, b)] = keep;
+            members[keep] += members[gone];
+            members[gone] = 0;
+            while (max_id > 0 && members[max_id] == 0) max_id--;
+        }
+    }
+    int top = 0;
+    for (int i = 0; i < nn; i++) {
+        node_vox[i] = (int32_t)vox[i];
+        node_label[i] = cid[cl.find(i)];
+        top = std::max(top, node_label[i]);
+    }
+    *n_nodes = nn;
+    *n_labels = top;
+    return 0;
+}

@@ -174,11 +174,15 @@ def assemble_face(inputs, candidates, pa, block_fn=default_block_fn, **kwargs):
     block, foreground, mask, numinst, start = inputs.region(
         bb_start - margin, np.maximum(bb_stop, bb_start + 1) + margin, **kwargs)
     overlapping = np.concatenate([candidates[pa[:, 0]], candidates[pa[:, 1]]], axis=1)
-    # coordinates relative to the region actually loaded (the reference subtracts
-    # the UNclipped start, stitch_patch_graph.py:317-321, which shifts regions that
-    # touch the volume origin; see DESIGN.md "deviations")
-    rel_c = cleaned - start
-    rel_p = overlapping - np.tile(start, 2)
+    # The reference makes the coordinates relative to the UNclipped region start
+    # (stitch_patch_graph.py:317-321) although the region it loads is clipped at
+    # the volume origin, so faces within patchshape//2 of the origin are scored at
+    # centres shifted by the clipped amount.  Reproduced by default (the affinities
+    # and, with mws, the label ids depend on it); ppp_fix_face_origin=True uses the
+    # start of the region actually loaded.
+    origin = start if kwargs.get('ppp_fix_face_origin', False) else bb_start - margin
+    rel_c = cleaned - origin
+    rel_p = overlapping - np.tile(origin, 2)
     kw = dict(kwargs)
     kw.update(skipRanking=True, skipThinCover=True, return_intermediates=True)
     _, aff = block_fn(block, foreground, mask, numinst, selected_patches=rel_c,
@@ -293,10 +297,10 @@ def stitch_arrays(inputs, block_fn=default_block_fn, paint_fn=None, **kwargs):
 
 
 def paint_global(inputs, pairs, aff, rank=0, world=1, **kwargs):
-    """connected components of the global graph on the device and painting of
-    the member patches (affGraphToInstances with sparse_labels,
-    stitch_patch_graph.py:380-396).  Each rank paints the nodes i = rank mod
-    world; the volumes are max-reduced."""
+    """connected components (or, with kwargs mws, the mutex watershed) of the
+    global graph and painting of the member patches (affGraphToInstances with
+    sparse_labels, stitch_patch_graph.py:380-396).  Each rank paints the nodes
+    i = rank mod world; the volumes are max-reduced."""
     import torch
     from . import cuda_code as cc
     ps = np.asarray(kwargs['patchshape'])
@@ -308,12 +312,18 @@ def paint_global(inputs, pairs, aff, rank=0, world=1, **kwargs):
     pd = torch.from_numpy(pairs.view(np.int32)).to(dev)
     ad = torch.from_numpy(aff).to(dev)
     n = len(pairs)
-    comp = torch.empty(V, dtype=torch.int32, device=dev)
-    ncomp = torch.zeros(1, dtype=torch.int32, device=dev)
-    scratch = torch.empty(cc.call('ppp_label_scratch_bytes', V, n), dtype=torch.uint8,
-                          device=dev)
-    cc.call('ppp_label_cc', cc.ptr(pd), cc.ptr(ad), n, cfg, cc.ptr(comp), cc.ptr(ncomp),
-            cc.ptr(scratch), stream)
+    if kwargs.get('mws', False):
+        from .assembly import mutex_watershed
+        node_vox, node_label, _ = mutex_watershed(pairs, aff, cfg)
+        comp = torch.zeros(V, dtype=torch.int32, device=dev)
+        comp[torch.from_numpy(node_vox).to(dev).long()] = torch.from_numpy(node_label).to(dev)
+    else:
+        comp = torch.empty(V, dtype=torch.int32, device=dev)
+        ncomp = torch.zeros(1, dtype=torch.int32, device=dev)
+        scratch = torch.empty(cc.call('ppp_label_scratch_bytes', V, n), dtype=torch.uint8,
+                              device=dev)
+        cc.call('ppp_label_cc', cc.ptr(pd), cc.ptr(ad), n, cfg, cc.ptr(comp), cc.ptr(ncomp),
+                cc.ptr(scratch), stream)
     Y, X = shape[1], shape[2]
     p64 = pairs.astype(np.int64)
     nodes = np.unique(np.concatenate([(p64[:, 0] * Y + p64[:, 1]) * X + p64[:, 2],

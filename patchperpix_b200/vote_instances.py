@@ -67,9 +67,6 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
         if kwargs.get(k, False):
             raise NotImplementedError("vote_instances option %r is outside "
                                       "the B200 hot path" % k)
-    if kwargs.get('mws', False) and not kwargs.get('return_intermediates', False):
-        raise NotImplementedError("mws labelling is a later row of the scope "
-                                  "table; use mws=False (thresholded CC)")
     patchshape = np.array(patchshape)
     rad = np.array([p // 2 for p in patchshape])
     ret_inter = kwargs.get('return_intermediates', False)
@@ -155,8 +152,20 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
     if kwargs.get('termAfterThinCover', False):
         return None, None
     # (5) patch graph
-    pairs_dev = torch.from_numpy(pairs.view(np.int32)).to(pred.device)
-    aff = asm.patch_graph(pairs_dev)
+    # centres handed in by a caller (stitcher) must lie inside the block: the
+    # reference would read out of bounds, here such pairs get affinity 0 (no edge)
+    inside = np.all(pairs.astype(np.int64) < np.tile(np.asarray(shape, np.int64), 2), axis=1)
+    if not inside.all():
+        logger.warning("%d patch pairs outside the block: affinity 0", int((~inside).sum()))
+        aff = torch.zeros(len(pairs), dtype=torch.float32, device=pred.device)
+        if inside.any():
+            sub = torch.from_numpy(np.ascontiguousarray(pairs[inside]).view(np.int32)).to(
+                pred.device)
+            aff[torch.from_numpy(np.nonzero(inside)[0]).to(pred.device)] = asm.patch_graph(sub)
+        pairs_dev = torch.from_numpy(pairs.view(np.int32)).to(pred.device)
+    else:
+        pairs_dev = torch.from_numpy(pairs.view(np.int32)).to(pred.device)
+        aff = asm.patch_graph(pairs_dev)
     if kwargs.get("save_patch_graph", False) or kwargs.get("termAfterPatchGraph", False):
         fn = os.path.splitext(os.path.basename(kwargs.get('affinities', 'block')))[0]
         np.save(os.path.join(kwargs['result_folder'], fn + "_selected_patch_pairs.npy"), pairs)
@@ -172,7 +181,7 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
         (pairs[:, 0].astype(np.int64) * Y + pairs[:, 1]) * X + pairs[:, 2],
         (pairs[:, 3].astype(np.int64) * Y + pairs[:, 4]) * X + pairs[:, 5]]))
     nodes = torch.from_numpy(nodes_np.astype(np.int32)).to(pred.device)
-    inst, ncomp = asm.label(pairs_dev, aff, nodes)
+    inst, ncomp = asm.label(pairs_dev, aff, nodes, mws=kwargs.get('mws', False))
     if ncomp > 65535:
         logger.warning("%d components do not fit the reference's uint16 labels", ncomp)
     inst = _unpad(inst)

@@ -30,12 +30,29 @@ def _load():
     return g, kw, inputs
 
 
-def _check(g, inst, fg, info):
+def _check(g, inst, fg, info, aff_tol=0.0):
     assert np.array_equal(inst.astype(np.uint16), g['instances'])
     assert np.array_equal(np.squeeze(fg).astype(np.uint16), g['foreground'])
     # per-block and per-face intermediates, in volume coordinates
     n_ref = sum(len(v) for k, v in g.items() if k.startswith('blk/') and k.endswith('aff_graph_mat'))
     assert info['n_edges'] == n_ref
+    # every stored pair list / affinity vector (blocks are stored block-relative,
+    # stitch_patch_graph.py:650, faces in volume coordinates, :338-347)
+    mine = {}
+    for p, a in zip(info['pairs'], info['aff']):
+        mine.setdefault(tuple(int(x) for x in p), []).append(float(a))
+    for k in g:
+        if not k.endswith('patch_pairs'):
+            continue
+        pp = g[k].astype(np.int64)
+        aa = g[k.replace('patch_pairs', 'aff_graph_mat')]
+        name = k.split('/')[1:-1]
+        if len(name) == 1:
+            pp = pp + np.tile([int(v) for v in name[0].split('_')], 2)
+        for p, a in zip(pp, aa):
+            got = mine.get(tuple(int(x) for x in p))
+            assert got is not None, (k, p)
+            assert min(abs(float(a) - v) for v in got) <= aff_tol * max(1.0, abs(float(a))), (k, p, a, got)
 
 
 def test_blockwise_host_logic_with_oracle_engine():
@@ -53,11 +70,29 @@ def test_blockwise_host_logic_with_oracle_engine():
         assert (mine[:, None, :] == ref_global[None, :, :]).all(-1).any(0).all()
 
 
+def test_blockwise_mws_with_oracle_engine():
+    """same run with the mutex-watershed partition of the global graph."""
+    from oracle import host_logic
+    g, kw, inputs = _load()
+    want = np.load(os.path.join(gu.GOLD, 'mws_cases.npz'))['blockwise_inst']
+    inst, _, _ = spg.stitch_arrays(inputs, block_fn=host_logic.oracle_block_fn,
+                                   paint_fn=host_logic.oracle_paint_fn, **dict(kw, mws=True))
+    assert np.array_equal(inst.astype(np.uint16), want)
+
+
+@pytest.mark.gpu
+def test_blockwise_mws_cuda():
+    g, kw, inputs = _load()
+    want = np.load(os.path.join(gu.GOLD, 'mws_cases.npz'))['blockwise_inst']
+    inst, _, _ = spg.stitch_arrays(inputs, **dict(kw, mws=True))
+    assert np.array_equal(inst.astype(np.uint16), want)
+
+
 @pytest.mark.gpu
 def test_blockwise_cuda_end_to_end():
     g, kw, inputs = _load()
     inst, fg, info = spg.stitch_arrays(inputs, **kw)
-    _check(g, inst, fg, info)
+    _check(g, inst, fg, info, aff_tol=1e-5)
 
 
 def _gloo_worker(rank, world, port, q):

@@ -1,0 +1,85 @@
+"""mutex-watershed labelling (kwargs mws=True, the flylight default) against
+vectors recorded from the unmodified reference (tools/gen_golden.py mws):
+graph_mws.mws on seeded random graphs and affGraphToInstances(mws=True) on the
+recorded pairs / affinities of every golden case."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import golden_util
+from patchperpix_b200 import cuda_code as cc
+from patchperpix_b200.assembly import mutex_watershed
+
+MWS = dict(np.load(os.path.join(golden_util.GOLD, 'mws_cases.npz')))
+N_RANDOM = int(MWS['n_random'])
+
+
+def _graph(gi):
+    k = 'rnd/%02d/' % gi
+    return MWS[k + 'pairs'], MWS[k + 'aff'], MWS[k + 'nodes'], MWS[k + 'labels']
+
+
+@pytest.mark.parametrize('gi', range(N_RANDOM))
+def test_oracle_mws_random_graphs(gi):
+    import networkx as nx
+    from oracle import host_logic
+    pairs, aff, nodes, labels = _graph(gi)
+    g = nx.Graph()
+    for i, a in enumerate(aff):
+        if a != 0:
+            g.add_edge(tuple(int(v) for v in pairs[i, :3]),
+                       tuple(int(v) for v in pairs[i, 3:6]), aff=a)
+    assert [list(n) for n in g.nodes()] == nodes.tolist()
+    lab = {}
+    for k, comp in enumerate(host_logic.mutex_watershed(g)):
+        for n in comp:
+            lab[n] = k + 1
+    got = np.array([lab.get(tuple(int(v) for v in n), 0) for n in nodes], np.int32)
+    assert np.array_equal(got, labels)
+
+
+@pytest.mark.parametrize('gi', range(N_RANDOM))
+def test_cabi_mws_random_graphs(gi):
+    """ppp_mws_host is host code: it runs without a GPU."""
+    pairs, aff, nodes, labels = _graph(gi)
+    Z, Y, X = 4, 40, 40
+    cfg = cc.make_cfg((Z, Y, X), (1, 3, 3), patch_threshold=0.5, fc_threshold=0.5)
+    vox, lab, top = mutex_watershed(pairs, aff, cfg)
+    want_vox = (nodes[:, 0].astype(np.int64) * Y + nodes[:, 1]) * X + nodes[:, 2]
+    assert np.array_equal(vox, want_vox)          # node insertion order
+    assert np.array_equal(lab, labels)            # same ids, gaps included
+    assert top == (labels.max() if len(labels) else 0)
+
+
+def test_cabi_mws_empty():
+    cfg = cc.make_cfg((1, 8, 8), (1, 3, 3), patch_threshold=0.5, fc_threshold=0.5)
+    vox, lab, top = mutex_watershed(np.zeros((0, 6), np.uint32), np.zeros(0, np.float32), cfg)
+    assert len(vox) == 0 and len(lab) == 0 and top == 0
+    # only zero affinities: no edge enters the graph (aff_patch_graph.py:36)
+    vox, lab, top = mutex_watershed(np.ones((3, 6), np.uint32), np.zeros(3, np.float32), cfg)
+    assert len(vox) == 0 and top == 0
+
+
+@pytest.mark.parametrize('name', golden_util.NAMES)
+def test_oracle_mws_instances(name):
+    from oracle import host_logic
+    g, kw, ps, pred = golden_util.load(name)
+    inst, _ = host_logic.label_instances(
+        g['pairs'], g['aff'], pred, ps, ps // 2, pred.shape[1:],
+        np.float32(kw['patch_threshold']), mws=True)
+    assert np.array_equal(inst, MWS['inst/' + name])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', golden_util.NAMES)
+def test_gpu_mws_instances(name):
+    """to_instance_seg(mws=True) end to end on the device."""
+    from patchperpix_b200 import vote_instances as vi
+    g, kw, ps, pred = golden_util.load(name)
+    kw = dict(kw, mws=True)
+    mid = int(np.prod(ps)) // 2
+    fg = pred[mid] > kw['patch_threshold']
+    inst, _ = vi.to_instance_seg(pred.copy(), fg.copy(), fg.copy(), g['numinst'].copy(),
+                                 ps.copy(), **kw)
+    assert np.array_equal(inst, MWS['inst/' + name])

@@ -202,9 +202,10 @@ class Recorder:
             self.d['pairs'] = np.array(arrs[3])
 
 
-def run_blockwise(S):
+def run_blockwise(S, mws=False):
     """the reference's blockwise driver (stitch_patch_graph.main) on an
-    in-memory zarr stand-in (oracle/ref_runner.FakeGroup)."""
+    in-memory zarr stand-in (oracle/ref_runner.FakeGroup).  mws: only return
+    the label volume of a run with the mutex-watershed partition."""
     import shutil
     sp = ref_runner.load_stitch_module(S)
     ps = np.array([5, 5, 5])
@@ -223,12 +224,14 @@ def run_blockwise(S):
         aff_key='volumes/pred_affs', numinst_key='volumes/pred_numinst', fg_key=None,
         numinst_threshs=[0.9, 0.1], only_bb=False, output_format='hdf',
         num_parallel_blocks=1, ignore_small_comps=0, skeletonize_foreground=False,
-        remove_small_comps=0, res_key='vote_instances')
+        remove_small_comps=0, res_key='vote_instances', mws=mws)
     del kw['result_folder']
     t0 = time.time()
     sp.main(pred_path, result_folder=os.path.join(root, 'out'), **kw)
     dt = time.time() - t0
     out = ref_runner.FakeGroup.open(os.path.join(root, 'out', 'sample.hdf'))
+    if mws:
+        return np.asarray(out['vote_instances'])
     blk = ref_runner.FakeGroup.open(os.path.join(root, 'out', 'sample.zarr'))
     import hashlib
     res = dict(
@@ -249,7 +252,71 @@ def run_blockwise(S):
         os.path.getsize(fn) / 1e6))
 
 
+def run_mws(S):
+    """mutex-watershed labelling (kwargs mws=True, the flylight default): the
+    reference's setAffgraph + affGraphToInstances on the recorded pairs / aff of
+    every case, plus graph_mws.mws on seeded random graphs (ties, self loops,
+    repeated pairs) that exercise the id bookkeeping."""
+    from tests import golden_util
+    apg = S.mods['aff_patch_graph']
+    g2l = S.mods['graph_to_labeling']
+    res = {}
+    for name in golden_util.NAMES:
+        g, kw, ps, pred = golden_util.load(name)
+        graph = apg.setAffgraph(g['aff'], g['pairs'])
+        inst = np.zeros(pred.shape[1:], np.uint16)
+        inst, _ = g2l.affGraphToInstances(
+            graph, pred, ps, ps // 2, None, None, inst, g['gate'], mws=True,
+            patch_threshold=kw['patch_threshold'], debug=False)
+        res['inst/' + name] = inst
+        print('mws %-24s inst=%d (cc: %d)' % (name, len(np.unique(inst)) - 1,
+                                             len(np.unique(g['instances'])) - 1))
+    rng = np.random.default_rng(99)
+    n_graphs = 24
+    for gi in range(n_graphs):
+        nn = int(rng.integers(6, 160))
+        coords = np.stack([rng.integers(0, 4, nn), rng.integers(0, 40, nn),
+                           rng.integers(0, 40, nn)], 1).astype(np.uint32)
+        coords = np.unique(coords, axis=0)
+        rng.shuffle(coords)
+        nn = len(coords)
+        ne = int(nn * rng.uniform(1.0, 4.0))
+        a = rng.integers(0, nn, ne)
+        b = rng.integers(0, nn, ne)
+        w = rng.normal(0.15, 0.5, ne).astype(np.float32)
+        if gi % 3 == 0:
+            w = np.round(w * 4) / 4                  # many ties and exact zeros
+        if gi % 4 == 1:
+            w = np.abs(w) * np.where(rng.random(ne) < 0.15, -1, 1).astype(np.float32)
+        pairs = np.concatenate([coords[a], coords[b]], 1).astype(np.uint32)
+        graph = apg.setAffgraph(w, pairs)
+        ccs = S.mods['graph_mws'].mws(graph)
+        lab = {}
+        for k, cc in enumerate(ccs):
+            for nd in cc:
+                lab[tuple(int(v) for v in nd)] = k + 1
+        nodes = np.array([list(nd) for nd in graph.nodes()], np.int32).reshape(-1, 3)
+        labels = np.array([lab.get(tuple(int(v) for v in nd), 0) for nd in graph.nodes()],
+                          np.int32)
+        res['rnd/%02d/pairs' % gi] = pairs
+        res['rnd/%02d/aff' % gi] = w
+        res['rnd/%02d/nodes' % gi] = nodes
+        res['rnd/%02d/labels' % gi] = labels
+        print('mws random %02d nodes=%d edges=%d comps=%d max=%d' % (
+            gi, len(nodes), graph.number_of_edges(), len(set(labels[labels > 0])),
+            labels.max() if len(labels) else 0))
+    res['n_random'] = np.int32(n_graphs)
+    res['blockwise_inst'] = run_blockwise(ref_runner.RefSession(), mws=True)
+    print('mws blockwise inst=%d' % (len(np.unique(res['blockwise_inst'])) - 1))
+    fn = os.path.join(GOLD, 'mws_cases.npz')
+    np.savez_compressed(fn, **res)
+    print('mws_cases %.2f MB' % (os.path.getsize(fn) / 1e6))
+
+
 def main():
+    if sys.argv[1:] == ['mws']:
+        run_mws(ref_runner.RefSession())
+        return 0
     if sys.argv[1:] == ['blockwise']:
         S = ref_runner.RefSession()
         run_blockwise(S)
