@@ -291,11 +291,15 @@ def main():
     clocks = sampler.summary()
 
     # ---- end to end: pinned host inputs -> labels on the host -----------------
-    pred_h = torch.empty(pred.shape, dtype=torch.float32).pin_memory()
+    # the prediction as the predict step stores it: float16 [P,Z,Y,X]
+    # (predict_no_gp.py:243-257); to_instance_seg widens it on the device, which is
+    # the exact conversion loadAffinities does on the host (utilVoteInstances.py:136-250)
+    pred_h = torch.empty(pred.shape, dtype=torch.float16).pin_memory()
     pred_h.copy_(pred)
+    assert torch.equal(pred_h.to(dev).float(), pred), "synthetic input is not f16-exact"
     fg_h = fg.cpu().pin_memory()
     numinst_h = torch.from_numpy(numinst).pin_memory()
-    h2d = pred_h.numel() * 4 + fg_h.numel() * 2 + numinst_h.numel()
+    h2d = pred_h.numel() * 2 + fg_h.numel() * 2 + numinst_h.numel()
     d2h = fg_h.numel() * 2 + fg_h.numel()          # u16 labels + u8 foreground
     for _ in range(2):
         vi.to_instance_seg(pred_h, fg_h, fg_h, numinst_h, ps, **KW)
@@ -335,7 +339,8 @@ def main():
                     flags='flylight [vote_instances] defaults, mws=False'),
         e2e=dict(value=tot_fg / (e2e_ms * 1e-3) / 1e6, unit='Mvoxels/s',
                  h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                 ms_per_step=e2e_ms),
+                 ms_per_step=e2e_ms,
+                 input='float16 [P,Z,Y,X] pinned host buffer (the stored form), widened on the device'),
         gpu_launches=n_launch, clocks=clocks,
         roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
                       frac=achieved / peak, traffic=None, kernel='ppp_consensus',

@@ -325,7 +325,7 @@ rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ f
 }
 
 // sort key: number of float additions of a centre, descending
-__global__ void rank_work_kernel(const int32_t* __restrict__ meta, int64_t F,
+__global__ void rank_work_kernel(const int32_t* __restrict__ meta, int64_t F, int shift,
                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -333,7 +333,7 @@ __global__ void rank_work_kernel(const int32_t* __restrict__ meta, int64_t F,
     int n = meta[r * 4], nH = meta[r * 4 + 1];
     uint32_t work = (n > 0 && nH > 0)
         ? (uint32_t)nH * (uint32_t)(n - 1) - ((uint32_t)nH * (uint32_t)(nH - 1)) / 2 : 0u;
-    keys[r] = ~work;
+    keys[r] = ~(work >> shift);
     vals[r] = (uint32_t)r;
 }
 
@@ -384,7 +384,7 @@ extern "C" int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fg
     size_t stb = work_sort_bytes(F);
     rank_lists_kernel<<<(unsigned)((F + 3) / 4), 128, 0, s>>>(dp, flags, rowvox, F, *cfg, lists,
                                                               hlists, llists, meta);
-    rank_work_kernel<<<(unsigned)((F + 255) / 256), 256, 0, s>>>(meta, F, keys, vals);
+    rank_work_kernel<<<(unsigned)((F + 255) / 256), 256, 0, s>>>(meta, F, cfg->reserved & 31, keys, vals);
     cub::DeviceRadixSort::SortPairs(sort_tmp, stb, keys, keys_out, vals, perm, (int)F, 0, 32, s);
     size_t smem = (size_t)RR_WARPS * RR_CPW * sizeof(RankRow) + (size_t)g.P * 4 +
                   (size_t)(g.P + 1) * 2 + (size_t)RR_WARPS * RR_CPW * 33 * 4 + 32;
