@@ -131,27 +131,35 @@ rank_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
 // cover, hence the labels.  To stay label-identical these kernels reproduce the
 // exact sequence of float additions of the reference's loop nest (po1 over the
 // high pixels, po2 over the other gated pixels):
-//   rank_lists_kernel  compacts, per patch centre, the voting pixels (in po
-//                      order) and the sub-list of high pixels into scratch;
+//   rank_lists_kernel  compacts, per patch centre, its voting pixels in po
+//                      order: e_lin (position in the offset raster | high bit),
+//                      h_idx (list index of every high pixel) and, from both
+//                      ends of x_lin / x_row, the offset-raster position and the
+//                      consensus row of the background pixels (front) and of the
+//                      high pixels (back);
 //   rank_ref_kernel    one WARP owns RR_CPW centres.  Lane s < RR_CPW performs
 //                      the serial float adds of centre s; the values are
 //                      gathered by the whole warp, 32 consecutive terms of one
-//                      centre per coalesced request (all RR_CPW requests in
-//                      flight together), and handed over through a
-//                      transposition buffer.  Skipped terms are fed as +0.0f,
-//                      which leaves a float sum unchanged.
+//                      centre per coalesced request (4 requests in flight per
+//                      lane), and handed over through a transposition buffer.
+//                      A high pixel p1 contributes two segments: the background
+//                      pixels before it (reversed slot, row of p2) and all
+//                      voting pixels after it (row of p1).  Missing terms are
+//                      fed as 0.0f, which leaves a float sum unchanged.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 rank_lists_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
-                  const int32_t* __restrict__ rowvox, int64_t F, ppp_cfg cfg,
-                  uint16_t* __restrict__ lists, uint16_t* __restrict__ hlists,
-                  uint16_t* __restrict__ llists, int32_t* __restrict__ meta)
+                  const int32_t* __restrict__ fgidx, const int32_t* __restrict__ rowvox,
+                  int64_t F, ppp_cfg cfg, uint16_t* __restrict__ e_lin,
+                  uint16_t* __restrict__ h_idx, uint16_t* __restrict__ x_lin,
+                  int32_t* __restrict__ x_row, int32_t* __restrict__ meta)
 {
     Geo g = make_geo(cfg);
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= F) return;
     const int vc = rowvox[row];
+    const int64_t loff = row * g.P;
     int n = 0, nH = 0, nG = 0;
     if (flags[vc] & PPP_FLAG_CENTRE) {
         int cz, cy, cx;
@@ -160,21 +168,32 @@ rank_lists_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flag
             int po = base + lane;
             float d = 0.0f;
             bool gated = false;
+            int lin = 0, prow = -1;
             if (po < g.P) {
                 int qz, qy, qx;
                 po_decode(g, po, qz, qy, qx);
                 d = dp[dp_index(g, F, row, po)];
                 int pv = ((cz + qz - g.rz) * g.Y + (cy + qy - g.ry)) * g.X + (cx + qx - g.rx);
                 gated = (flags[pv] & PPP_FLAG_GATED) != 0;
+                lin = po_lin(g, qz, qy, qx);
+                if (d != 0.0f) prow = fgidx[pv];
             }
             unsigned bal = __ballot_sync(0xffffffffu, d != 0.0f);
             unsigned balh = __ballot_sync(0xffffffffu, d > 0.0f);
             unsigned lt = (1u << lane) - 1u;
             if (d != 0.0f) {
                 int idx = n + __popc(bal & lt);
-                lists[row * g.P + idx] = (uint16_t)(po | (d > 0.0f ? 0x8000 : 0));
-                if (d > 0.0f) hlists[row * g.P + nH + __popc(balh & lt)] = (uint16_t)idx;
-                else llists[row * g.P + (n - nH) + __popc((bal & ~balh) & lt)] = (uint16_t)po;
+                e_lin[loff + idx] = (uint16_t)(lin | (d > 0.0f ? 0x8000 : 0));
+                if (d > 0.0f) {
+                    int h = nH + __popc(balh & lt);
+                    h_idx[loff + h] = (uint16_t)idx;
+                    x_lin[loff + g.P - 1 - h] = (uint16_t)lin;
+                    x_row[loff + g.P - 1 - h] = prow;
+                } else {
+                    int q = (n - nH) + __popc((bal & ~balh) & lt);
+                    x_lin[loff + q] = (uint16_t)lin;
+                    x_row[loff + q] = prow;
+                }
             }
             n += __popc(bal);
             nH += __popc(balh);
@@ -185,47 +204,44 @@ rank_lists_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flag
 }
 
 #define RR_WARPS 4
-#define RR_CPW 4
+#define RR_ST 36            // floats per staging row (16-byte aligned, conflict-free for 8 lanes)
 
-// what every lane needs to know about the current high row of one centre
-struct __align__(16) RankRow {
-    const float* cbase;     // cons + row(p1)*K - lin(p1) - 1 : slot of (p1, p2) = cbase[lin(p2)]
-    int64_t loff;           // row * P: offset of this centre in lists / llists
-    int i;                  // list index of the high pixel p1
-    int t0;                 // first term of this round
-    int lb;                 // background entries before p1 (reversed terms come first)
-    int nslots;             // lb + (n - 1 - i)
-    int li;                 // lin(p1)
-    int vc;                 // centre voxel
-    int pad0, pad1;
+// the segment of terms every lane gathers next for one centre: term t of the
+// segment is +-cons[base + xrow[rp + t] * K + sgn * (lst[lp + t] & 0x7fff)].
+// Indices, not pointers: loads through them stay LDG (predicated, no branches).
+// IdxT = int32_t when every index space fits (one 16-byte descriptor), else int64_t.
+template <typename IdxT>
+struct __align__(16) RankSeg {
+    IdxT base;              // "after": row(p1)*K - lin(p1) - 1;  "before": lin(p1) - 1
+    IdxT lp;                // next entry in lst (e_lin part for "after", x_lin part for "before")
+    IdxT rp;                // "before": next entry in x_row (rows of the background pixels)
+    int cb;                 // terms left in this segment (<= 0: nothing to gather) * 2 + before
 };
 
+// RR_CPW centres per warp, RR_T requests of 32 terms per centre and round, RR_B
+// centres gathered at a time.  lst = [e_lin | h_idx | x_lin] (three u16 arrays of
+// F*P entries, `lb16` entries apart).
+template <int RR_CPW, int RR_B, int RR_T, typename IdxT>
 __global__ void __launch_bounds__(RR_WARPS * 32)
-rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
-                const int32_t* __restrict__ rowvox, const float* __restrict__ cons,
-                const uint16_t* __restrict__ lists, const uint16_t* __restrict__ hlists,
-                const uint16_t* __restrict__ llists, const int32_t* __restrict__ meta,
-                const uint32_t* __restrict__ perm, int64_t F, ppp_cfg cfg,
-                float* __restrict__ score)
+rank_ref_kernel(const int32_t* __restrict__ rowvox, const float* __restrict__ cons,
+                const uint16_t* __restrict__ lst, int64_t lb16,
+                const int32_t* __restrict__ x_row,
+                const int32_t* __restrict__ meta, const uint32_t* __restrict__ perm,
+                int64_t F, ppp_cfg cfg, float* __restrict__ score)
 {
+    constexpr int ST = 32 * RR_T + 4;     // staging row: 16-byte aligned, conflict-free
+    constexpr int TPR = 32 * RR_T;        // terms per round
+    typedef RankSeg<IdxT> Seg;
     Geo g = make_geo(cfg);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    RankRow* s_rows = (RankRow*)smem_raw;                       // [RR_WARPS][RR_CPW]
-    int32_t* tab_dv = (int32_t*)(s_rows + RR_WARPS * RR_CPW);   // [P] voxel delta of patch pixel
-    uint16_t* tab_lin = (uint16_t*)(tab_dv + g.P);              // [P] position in the offset raster
-    float* stage = (float*)(tab_lin + g.P + (g.P & 1));         // [RR_WARPS][RR_CPW][33]
+    __shared__ Seg s_seg[RR_WARPS][RR_CPW];
+    __shared__ __align__(16) float s_stage[RR_WARPS][RR_CPW][ST];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int po = threadIdx.x; po < g.P; po += blockDim.x) {
-        int qz, qy, qx;
-        po_decode(g, po, qz, qy, qx);
-        tab_dv[po] = ((qz - g.rz) * g.Y + (qy - g.ry)) * g.X + (qx - g.rx);
-        tab_lin[po] = (uint16_t)po_lin(g, qz, qy, qx);
-    }
-    __syncthreads();
-    float* mystage = stage + w * RR_CPW * 33;
-    RankRow* myrows = s_rows + w * RR_CPW;
+    Seg* segs = s_seg[w];
+    float (*stage)[ST] = s_stage[w];
     const bool count_mode = (cfg.rank_flags & 2) != 0;
     const int64_t ngroups = (F + RR_CPW - 1) / RR_CPW;
+    const IdxT K = (IdxT)g.K;
+    const IdxT H_IDX = (IdxT)lb16, X_LIN = (IdxT)(2 * lb16);
 
     for (int64_t grp = (int64_t)blockIdx.x * RR_WARPS + w; grp < ngroups;
          grp += (int64_t)gridDim.x * RR_WARPS) {
@@ -234,92 +250,130 @@ rank_ref_kernel(const uint8_t* __restrict__ flags, const int32_t* __restrict__ f
         // together and the heavy warps start first)
         const int64_t slot = grp * RR_CPW + lane;
         const int64_t myrow = (lane < RR_CPW && slot < F) ? (int64_t)perm[slot] : F;
-        int n_s = -1, nH_s = 0, nG_s = 0, vc_s = 0;
-        if (lane < RR_CPW && myrow < F) {
+        int n_s = -1, nH_s = 0, nG_s = 0;
+        if (myrow < F) {
             n_s = meta[myrow * 4]; nH_s = meta[myrow * 4 + 1]; nG_s = meta[myrow * 4 + 2];
-            vc_s = rowvox[myrow];
         }
+        const IdxT loff = (IdxT)((myrow < F ? myrow : 0) * g.P);
         float acc = 0.0f;                 // running float sum of my centre
-        int cur_h = 0;                    // current high row (index into hlist)
+        int cur_h = 0;                    // current high pixel (index into h_idx)
+        int pend_after = 0, pend_i = 0;   // "after" segment still to come for cur_h
+        IdxT pend_base = 0;
         bool alive = n_s > 0 && nH_s > 0;
-        auto open_row = [&]() {           // owner lane: publish high row cur_h
-            const int i = hlists[myrow * g.P + cur_h];
-            const int ei = lists[myrow * g.P + i] & 0x7fff;
-            const int li = tab_lin[ei];
-            RankRow r;
-            r.cbase = cons + (int64_t)fgidx[vc_s + tab_dv[ei]] * g.K - li - 1;
-            r.loff = myrow * g.P;
-            r.i = i; r.t0 = 0; r.lb = i - cur_h; r.nslots = (i - cur_h) + (n_s - 1 - i);
-            r.li = li; r.vc = vc_s; r.pad0 = 0; r.pad1 = 0;
-            myrows[lane] = r;
+        auto open_after = [&](Seg& r) {
+            r.base = pend_base;
+            r.lp = loff + pend_i + 1;
+            r.rp = 0;                     // unused
+            r.cb = pend_after * 2;
+            pend_after = 0;
         };
-        if (alive) open_row();
-        __syncwarp();
-        while (true) {
-            const unsigned live = __ballot_sync(0xffffffffu, alive);
-            if (!live) break;
-            // ---- gather 32 consecutive terms of every live centre, in three phases
-            // (list entries, consensus values, hand-over) so that RR_CPW independent
-            // loads are in flight per lane ---------------------------------------------
-            int ej_[RR_CPW], li_[RR_CPW], vc_[RR_CPW];
-            const float* cb_[RR_CPW];
-            int st_[RR_CPW];                                     // 0 none, 1 after, 2 before
-            float val_[RR_CPW];
-#pragma unroll
-            for (int u = 0; u < RR_CPW; u++) {
-                const RankRow r = myrows[u];                     // broadcast
-                const int tt = r.t0 + lane;
-                const bool ok = ((live >> u) & 1u) && tt < r.nslots;
-                const bool before = tt < r.lb;
-                st_[u] = ok ? (before ? 2 : 1) : 0;
-                cb_[u] = r.cbase; li_[u] = r.li; vc_[u] = r.vc;
-                ej_[u] = !ok ? 0 : (before ? (int)llists[r.loff + tt]
-                                           : (int)lists[r.loff + r.i + 1 + (tt - r.lb)]);
+        // descriptor of the NEXT high pixel, fetched one row ahead so that opening a
+        // row never waits on memory
+        int nx_i = 0, nx_li = 0, nx_row = 0;
+        auto fetch = [&](int h) {
+            if (h < nH_s) {
+                nx_i = lst[H_IDX + loff + h];
+                nx_li = lst[X_LIN + loff + g.P - 1 - h];
+                nx_row = x_row[loff + g.P - 1 - h];
             }
-#pragma unroll
-            for (int u = 0; u < RR_CPW; u++) {
-                const int pj = ej_[u] & 0x7fff;
-                const int lj = tab_lin[pj];
-                float v3 = 0.0f;
-                if (st_[u] == 1) v3 = cb_[u][lj];
-                else if (st_[u] == 2)
-                    v3 = cons[(int64_t)fgidx[vc_[u] + tab_dv[pj]] * g.K + li_[u] - lj - 1];
-                val_[u] = v3;
-            }
-#pragma unroll
-            for (int u = 0; u < RR_CPW; u++) {
-                const bool hj = (ej_[u] & 0x8000) != 0;
-                float v3 = val_[u], val = 0.0f;
-                if (st_[u] == 1) {
-                    // rankPatches.cu:88-100 (both high) / :102-137 (high, background)
-                    if (count_mode) v3 = (v3 != 0.0f) ? copysignf(1.0f, v3) : (hj ? -1.0f : 1.0f);
-                    val = hj ? v3 : -v3;
-                } else if (st_[u] == 2) {
-                    // background pixel before the high one: reversed slot (:109-126)
-                    if (count_mode) v3 = (v3 != 0.0f) ? copysignf(1.0f, v3) : 1.0f;
-                    val = -v3;
+        };
+        auto open_row = [&]() {           // owner lane: publish the next non-empty segment
+            Seg r;
+            r.base = 0; r.lp = 0; r.rp = 0; r.cb = 0;
+            while (cur_h < nH_s) {
+                const int i = nx_i, li = nx_li;
+                const IdxT hrow = nx_row;
+                fetch(cur_h + 1);
+                const int lb = i - cur_h, na = n_s - 1 - i;
+                if (lb + na > 0) {
+                    pend_base = hrow * K - li - 1;
+                    pend_after = na; pend_i = i;
+                    if (lb > 0) {
+                        r.base = li - 1;
+                        r.lp = X_LIN + loff; r.rp = loff; r.cb = lb * 2 + 1;
+                    } else open_after(r);
+                    break;
                 }
-                mystage[u * 33 + lane] = val;
+                cur_h++;
+            }
+            if (cur_h >= nH_s) { alive = false; r.cb = 0; }
+            segs[lane] = r;
+        };
+        if (alive) fetch(0);
+        if (lane < RR_CPW) {
+            if (alive) open_row();
+            else { Seg r; r.base = 0; r.lp = 0; r.rp = 0; r.cb = 0; segs[lane] = r; }
+        }
+        __syncwarp();
+        while (__ballot_sync(0xffffffffu, alive)) {
+            // ---- gather TPR consecutive terms of every centre, RR_B centres at a time,
+            // in three phases (list entries, consensus values, hand-over) so that
+            // RR_B * RR_T independent loads are in flight per lane; branch-free ---------
+#pragma unroll
+            for (int u0 = 0; u0 < RR_CPW; u0 += RR_B) {
+                int e_[RR_B][RR_T], r_[RR_B][RR_T], bf_[RR_B];
+                IdxT b_[RR_B];
+                float v_[RR_B][RR_T];
+#pragma unroll
+                for (int u = 0; u < RR_B; u++) {
+                    const Seg d = segs[u0 + u];                   // broadcast
+                    const int cnt = d.cb >> 1;
+                    b_[u] = d.base; bf_[u] = d.cb & 1;
+#pragma unroll
+                    for (int t = 0; t < RR_T; t++) {
+                        const bool ok = lane + 32 * t < cnt;
+                        e_[u][t] = ok ? (int)lst[d.lp + lane + 32 * t] : -1;
+                        r_[u][t] = (ok && bf_[u]) ? x_row[d.rp + lane + 32 * t] : 0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < RR_B; u++)
+#pragma unroll
+                    for (int t = 0; t < RR_T; t++) {
+                        const int le = e_[u][t] & 0x7fff;
+                        const IdxT idx = b_[u] + (IdxT)r_[u][t] * K + (bf_[u] ? -le : le);
+                        v_[u][t] = e_[u][t] >= 0 ? cons[idx] : 0.0f;
+                    }
+#pragma unroll
+                for (int u = 0; u < RR_B; u++)
+#pragma unroll
+                    for (int t = 0; t < RR_T; t++) {
+                        // rankPatches.cu:88-100 (both high), :102-137 (high, background),
+                        // :109-126 (background before the high pixel: reversed slot).  A
+                        // "before" entry never carries the high bit.
+                        const bool hj = (e_[u][t] & 0x8000) != 0;
+                        float v3 = v_[u][t];
+                        if (count_mode)
+                            v3 = (v3 != 0.0f) ? copysignf(1.0f, v3) : (hj ? -1.0f : 1.0f);
+                        float val = hj ? v3 : -v3;
+                        stage[u0 + u][lane + 32 * t] = e_[u][t] >= 0 ? val : 0.0f;
+                    }
             }
             __syncwarp();
             // ---- serial float adds of my centre, in the reference's order --------------
             if (alive) {
-                const float* st = mystage + lane * 33;
+                const float4* st = (const float4*)stage[lane];
 #pragma unroll
-                for (int q = 0; q < 32; q++) acc += st[q];
-                const int t1 = myrows[lane].t0 + 32;
-                if (t1 >= myrows[lane].nslots) {                 // next high row
+                for (int q = 0; q < 8 * RR_T; q++) {
+                    float4 t = st[q];
+                    acc += t.x; acc += t.y; acc += t.z; acc += t.w;
+                }
+                Seg& r = segs[lane];
+                if ((r.cb >> 1) > TPR) {
+                    r.cb -= 2 * TPR; r.lp += TPR; r.rp += TPR;
+                } else if ((r.cb & 1) && pend_after > 0) {
+                    open_after(r);
+                } else {
                     cur_h++;
-                    if (cur_h >= nH_s) alive = false;
-                    else open_row();
-                } else myrows[lane].t0 = t1;
+                    open_row();
+                }
             }
             __syncwarp();
         }
         if (n_s >= 0) {
             unsigned h = (unsigned)nH_s, gg = (unsigned)nG_s;
             unsigned fgCnt = h * gg - h - (h * (h - 1)) / 2;
-            score[vc_s] = (cfg.rank_flags & 1) ? acc / (float)(fgCnt > 1 ? fgCnt : 1) : acc;
+            score[rowvox[myrow]] = (cfg.rank_flags & 1) ? acc / (float)(fgCnt > 1 ? fgCnt : 1) : acc;
         }
     }
 }
@@ -349,7 +403,8 @@ extern "C" int64_t ppp_rank_scratch_bytes(const ppp_cfg* cfg, int64_t F)
 {
     Geo g = make_geo(*cfg);
     if (F < 1) F = 1;
-    return 3 * ((F * g.P * 2 + 255) / 256) * 256 + ((F * 16 + 255) / 256) * 256 +
+    // e_lin, h_idx, x_lin (u16) + x_row (i32) + meta + keys/vals x4 + sort temp
+    return 5 * ((F * g.P * 2 + 255) / 256) * 256 + ((F * 16 + 255) / 256) * 256 +
            4 * ((F * 4 + 255) / 256) * 256 + ((work_sort_bytes(F) + 255) / 256) * 256 + 256;
 }
 
@@ -368,34 +423,49 @@ extern "C" int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fg
                                                             cons, F, *cfg, score);
         return ppp_check("ppp_rank(fast)");
     }
-    if (g.P >= 32768) return ppp_fail(-1, "ppp_rank: patch too large");
+    if (2 * g.K + 1 >= 32768) return ppp_fail(-1, "ppp_rank: patch too large");
     if (scratch == nullptr) return ppp_fail(-1, "ppp_rank: scratch required");
     size_t lb = ((F * g.P * 2 + 255) / 256) * 256;
-    uint16_t* lists = (uint16_t*)scratch;
-    uint16_t* hlists = (uint16_t*)((char*)scratch + lb);
-    uint16_t* llists = (uint16_t*)((char*)scratch + 2 * lb);
-    int32_t* meta = (int32_t*)((char*)scratch + 3 * lb);
+    uint16_t* e_lin = (uint16_t*)scratch;
+    uint16_t* h_idx = (uint16_t*)((char*)scratch + lb);
+    uint16_t* x_lin = (uint16_t*)((char*)scratch + 2 * lb);
+    int32_t* x_row = (int32_t*)((char*)scratch + 3 * lb);
+    int32_t* meta = (int32_t*)((char*)scratch + 5 * lb);
     size_t mb = ((F * 16 + 255) / 256) * 256, fb = ((F * 4 + 255) / 256) * 256;
-    uint32_t* keys = (uint32_t*)((char*)scratch + 3 * lb + mb);
+    uint32_t* keys = (uint32_t*)((char*)scratch + 5 * lb + mb);
     uint32_t* keys_out = keys + fb / 4;
     uint32_t* vals = keys_out + fb / 4;
     uint32_t* perm = vals + fb / 4;
-    void* sort_tmp = (char*)scratch + 3 * lb + mb + 4 * fb;
+    void* sort_tmp = (char*)scratch + 5 * lb + mb + 4 * fb;
     size_t stb = work_sort_bytes(F);
-    rank_lists_kernel<<<(unsigned)((F + 3) / 4), 128, 0, s>>>(dp, flags, rowvox, F, *cfg, lists,
-                                                              hlists, llists, meta);
+    rank_lists_kernel<<<(unsigned)((F + 3) / 4), 128, 0, s>>>(dp, flags, fgidx, rowvox, F, *cfg,
+                                                              e_lin, h_idx, x_lin, x_row, meta);
     rank_work_kernel<<<(unsigned)((F + 255) / 256), 256, 0, s>>>(meta, F, cfg->reserved & 31, keys, vals);
     cub::DeviceRadixSort::SortPairs(sort_tmp, stb, keys, keys_out, vals, perm, (int)F, 0, 32, s);
-    size_t smem = (size_t)RR_WARPS * RR_CPW * sizeof(RankRow) + (size_t)g.P * 4 +
-                  (size_t)(g.P + 1) * 2 + (size_t)RR_WARPS * RR_CPW * 33 * 4 + 32;
-    cudaError_t e = cudaFuncSetAttribute(rank_ref_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return ppp_fail((int)e, "ppp_rank: smem attribute");
-    int64_t ngroups = (F + RR_CPW - 1) / RR_CPW;
-    int64_t nblk = (ngroups + RR_WARPS - 1) / RR_WARPS;
-    rank_ref_kernel<<<(unsigned)nblk, RR_WARPS * 32, smem, s>>>(flags, fgidx, rowvox, cons, lists,
-                                                               hlists, llists, meta, perm, F, *cfg,
-                                                               score);
+    // 32-bit indices when the list and consensus index spaces fit
+    const bool idx32 = 3 * (int64_t)(lb / 2) < 0x7fffffffLL &&
+                       (F + 1) * (int64_t)g.K + 0x8000 < 0x7fffffffLL;
+#define RR_LAUNCH(CPW, B, T)                                                                \
+    {                                                                                       \
+        int64_t ngroups = (F + CPW - 1) / CPW;                                              \
+        int64_t nblk = (ngroups + RR_WARPS - 1) / RR_WARPS;                                 \
+        if (idx32)                                                                          \
+            rank_ref_kernel<CPW, B, T, int32_t><<<(unsigned)nblk, RR_WARPS * 32, 0, s>>>(   \
+                rowvox, cons, e_lin, (int64_t)(lb / 2), x_row, meta, perm, F, *cfg, score); \
+        else                                                                                \
+            rank_ref_kernel<CPW, B, T, int64_t><<<(unsigned)nblk, RR_WARPS * 32, 0, s>>>(   \
+                rowvox, cons, e_lin, (int64_t)(lb / 2), x_row, meta, perm, F, *cfg, score); \
+    }
+    switch ((cfg->reserved >> 8) & 7) {
+    case 1: RR_LAUNCH(4, 4, 2); break;
+    case 2: RR_LAUNCH(4, 2, 2); break;
+    case 3: RR_LAUNCH(4, 4, 1); break;
+    case 4: RR_LAUNCH(2, 2, 2); break;
+    case 5: RR_LAUNCH(2, 2, 4); break;
+    case 6: RR_LAUNCH(8, 4, 2); break;
+    case 7: RR_LAUNCH(4, 2, 4); break;
+    default: RR_LAUNCH(4, 4, 4); break;
+    }
     return ppp_check("ppp_rank(reference order)");
 }
 
