@@ -43,9 +43,11 @@ KW = dict(patch_threshold=0.5, fc_threshold=0.5, cuda=True, blockwise=False,
           rank_norm_patch_score=True, rank_int_counter=False, patch_graph_norm_aff=True,
           overlapping_inst=True, skipThinCover=False)
 # kernels launched per C-ABI call (counted to report gpu_launches)
-LAUNCHES = dict(ppp_gate=1, ppp_compact=3, ppp_prepare_patches=2, ppp_consensus=3,
-                ppp_rank=3, ppp_rank_sort=5, ppp_cover=1, ppp_thin=1, ppp_patch_graph=1,
-                ppp_label_cc=9, ppp_paint=1)
+# (own kernels + the CUB radix-sort passes the library launches; checked against
+# the ncu launch list profiles/r1_v6_launches.csv: 42 per step)
+LAUNCHES = dict(ppp_gate=1, ppp_compact=3, ppp_prepare_patches=2, ppp_consensus=2,
+                ppp_rank=10, ppp_rank_sort=12, ppp_cover=1, ppp_thin=1, ppp_patch_graph=1,
+                ppp_label_cc=8, ppp_paint=1)
 
 
 def peaks():
@@ -206,6 +208,8 @@ def device_step(pred, fg, overlap, mask, ps, kw, timers=None):
     if timers is not None:
         timers[1].record()
     asm.rank()
+    if timers is not None:
+        timers[2].record()
     order = asm.ranked()
     sel = asm.cover(mask, order)
     sel = asm.thin(mask, sel)
@@ -274,7 +278,7 @@ def main():
         device_step(pred, fg, overlap, mask, ps, KW)
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     barrier()
     launches[0] = 0
     t0 = torch.cuda.Event(enable_timing=True)
@@ -288,6 +292,7 @@ def main():
     n_launch = launches[0] // steps
     ms = t0.elapsed_time(t1) / steps
     cons_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    rank_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     clocks = sampler.summary()
 
     # ---- end to end: pinned host inputs -> labels on the host -----------------
@@ -325,8 +330,17 @@ def main():
         return 0
 
     peak, how = peaks()
+    # algorithmic bytes per fg voxel: consensus = own patch (f32) +
+    # 1 gate byte + K x (f32 affinity + integer counter); rank = patch + K consensus
+    # values + 1 score
     b_unit = P * 4 + 1 + K * 8
     achieved = b_unit * nfg / (cons_ms * 1e-3) / 1e9
+    b_rank = P * 4 + K * 4 + 4
+    # DRAM bytes per launch of the same kernels from the committed ncu capture
+    traffic = {}
+    tp = os.path.join(ROOT, 'profiles', 'r1_v6_traffic.json')
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
     line = dict(
         metric='consensus+assembly fg Mvoxels/s', value=tot_fg / (ms * 1e-3) / 1e6,
         unit='Mvoxels/s', n_gpus=world, steps=steps, warmup=warm, ms_per_step=ms,
@@ -343,8 +357,19 @@ def main():
                  input='float16 [P,Z,Y,X] pinned host buffer (the stored form), widened on the device'),
         gpu_launches=n_launch, clocks=clocks,
         roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
-                      frac=achieved / peak, traffic=None, kernel='ppp_consensus',
-                      kernel_ms=cons_ms, bytes_per_fg_voxel=b_unit, peak_source=how),
+                      frac=achieved / peak, traffic=traffic.get('ppp_consensus'),
+                      kernel='ppp_consensus (consensus_count_kernel + consensus_rows_kernel)',
+                      kernel_ms=cons_ms, share_of_step=cons_ms / ms,
+                      bytes_per_fg_voxel=b_unit, peak_source=how,
+                      note='HBM is the bound SURVEY 8d assigns; the kernel itself is '
+                           'issue/latency-bound on ~1.8e10 pair visits (DESIGN.md section 6)'),
+        roofline_other=[dict(bound='hbm', kernel='ppp_rank (reference summation order)',
+                             kernel_ms=rank_ms, share_of_step=rank_ms / ms,
+                             bytes_per_fg_voxel=b_rank,
+                             achieved=b_rank * nfg / (rank_ms * 1e-3) / 1e9, peak=peak,
+                             unit='GB/s',
+                             frac=b_rank * nfg / (rank_ms * 1e-3) / 1e9 / peak,
+                             traffic=traffic.get('ppp_rank'))],
     )
     if not args.no_cpu_baseline:
         try:
