@@ -10,7 +10,8 @@ BUILD = os.path.join(HERE, '_build')
 SO = os.path.join(HERE, 'libppp_b200.so')
 SOURCES = ['ppp_api.cu', 'ppp_prep.cu', 'ppp_consensus.cu', 'ppp_rank.cu',
            'ppp_cover.cu', 'ppp_graph.cu', 'ppp_mws.cu', 'ppp_decoder.cu']
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
+EXTRA_DEFS = os.environ.get('PPP_EXTRA_DEFS', '').split()   # tuning experiments only
+NVCC_FLAGS = EXTRA_DEFS + ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
               '-std=c++17', '-Xcompiler', '-fPIC', '--use_fast_math=false',
               '-Xptxas', '-v']
 

@@ -240,8 +240,12 @@ consensus_bits_kernel(const float* __restrict__ dp, const unsigned long long* __
 // summation order -> deterministic, and bit-identical to the simple kernel.
 // ---------------------------------------------------------------------------
 #define CT_T 8
+#ifndef CT_THREADS
 #define CT_THREADS 256
+#endif
+#ifndef CT_NCCH
 #define CT_NCCH 64
+#endif
 #define CT_XMAX 2048
 #define CT_MAXTILES 512
 #define CT_MAXITEMS 6144
@@ -320,6 +324,18 @@ __device__ int ct_tiles_of_line(const uint8_t* __restrict__ flags, const int32_t
     return n;
 }
 
+#ifdef CT_PROFILE
+__device__ unsigned long long ct_prof[8];
+extern "C" int ppp_debug_ct_prof(unsigned long long* out, int reset)
+{
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(ct_prof, z, sizeof(z)); return 0; }
+    return (int)cudaMemcpyFromSymbol(out, ct_prof, 8 * sizeof(unsigned long long));
+}
+#define CT_TICK(i) if (tid == 0) { long long now_ = clock64(); atomicAdd(&ct_prof[i], (unsigned long long)(now_ - t_prof)); t_prof = now_; }
+#else
+#define CT_TICK(i)
+#endif
+
 template <int NOY>
 __global__ void __launch_bounds__(CT_THREADS)
 consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
@@ -350,6 +366,9 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
     const int nrows_off = (g.nz * g.ny - 1) / 2 + 1;             // offset rows >= (0,0)
     const int rlin_c = (g.nz * g.ny - 1) / 2;
     const int tid = threadIdx.x;
+#ifdef CT_PROFILE
+    long long t_prof = clock64();
+#endif
 
     // ---- tiles of the base line ----------------------------------------------
     const int nbt = ct_tiles_of_line(flags, fgidx, rowvox, bline, g.X, g.V, F, s_tmp, s_bt, s_scr);
@@ -404,20 +423,14 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
     const int cza = max(bz - g.rz, g.rz), czb = min(bz + g.rz, g.Z - 1 - g.rz);
     const int cya = max(by - g.ry, g.ry), cyb = min(by + g.ry, g.Y - 1 - g.ry);
     const int ncy = cyb - cya + 1, nlines = max(czb - cza + 1, 0) * max(ncy, 0);
-    const int bxmin = s_bt[0], bxmax = s_bt[nbt - 1] + T - 1;
-    const int cxa = max(bxmin - g.rx, g.rx), cxb = min(bxmax + g.rx, g.X - 1 - g.rx);
-    for (int l = tid; l < nlines; l += CT_THREADS) {
-        int cz = cza + l / ncy, cy = cya + l % ncy;
-        int64_t cline = ((int64_t)cz * g.Y + cy) * g.X;
-        int ra = 0, rb = 0;
-        if (cxb >= cxa) {
-            ra = rows_before(fgidx, cline + cxa, g.V, F);
-            rb = rows_before(fgidx, cline + cxb + 1, g.V, F);
-        }
-        s_ra[l] = ra; s_rb[l] = rb;
-    }
+    __shared__ int s_clo, s_chi;
     __syncthreads();
     const int nitems = s_nitems;
+    CT_TICK(0)
+#ifdef CT_PROFILE
+    if (tid == 0) { atomicAdd(&ct_prof[4], 1ull); atomicAdd(&ct_prof[5], (unsigned long long)nitems);
+                    atomicAdd(&ct_prof[6], (unsigned long long)((nitems + CT_THREADS - 1) / CT_THREADS)); }
+#endif
     if (nitems == 0 || nlines <= 0) return;
     unsigned phase0 = 0, phase1 = 0;
 
@@ -432,6 +445,24 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
         }
         // centres that can see a voxel of both windows
         const int my_clo = max(b0, p0) - g.rx, my_chi = min(b0, p0) + T - 1 + g.rx;
+        // ---- row ranges of the centre lines, restricted to the centres this batch
+        // of items can use (items are base-tile major: one x-neighbourhood) ----------
+        if (tid == 0) { s_clo = 0x7fffffff; s_chi = -0x7fffffff; }
+        __syncthreads();
+        if (have && my_chi >= my_clo) { atomicMin(&s_clo, my_clo); atomicMax(&s_chi, my_chi); }
+        __syncthreads();
+        const int cxa = max(s_clo, g.rx), cxb = min(s_chi, g.X - 1 - g.rx);
+        for (int l = tid; l < nlines; l += CT_THREADS) {
+            int cz = cza + l / ncy, cy = cya + l % ncy;
+            int64_t cline = ((int64_t)cz * g.Y + cy) * g.X;
+            int ra = 0, rb = 0;
+            if (cxb >= cxa) {
+                ra = rows_before(fgidx, cline + cxa, g.V, F);
+                rb = rows_before(fgidx, cline + cxb + 1, g.V, F);
+            }
+            s_ra[l] = ra; s_rb[l] = rb;
+        }
+        __syncthreads();
         float acc[T][T];
 #pragma unroll
         for (int j = 0; j < T; j++)
@@ -533,6 +564,7 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
             cur_nc = nxt_nc;
             cur_l = nxt_l;
         }
+        CT_TICK(1)
         // ---- epilogue: normalise with the integer counters and store -----------
         if (have) {
             int rlin = rlin_c + blockIdx.x * NOY + my_t;
@@ -561,6 +593,7 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
             }
         }
         __syncthreads();
+        CT_TICK(2)
     }
 }
 
