@@ -67,7 +67,8 @@ typedef struct ppp_cfg {
     int32_t rank_flags;         /* bit0 NORM_PATCH_RANK, bit1 COUNT_POS_NEG, bit2 fast
                                    parallel double sum instead of the reference's serial
                                    float order (scores then differ by its rounding) */
-    int32_t graph_flags;        /* bit0 NORM_PATCH_AFFINITY */
+    int32_t graph_flags;        /* bit0 NORM_PATCH_AFFINITY, bit2 parallel double sum instead of
+                                 * the reference's serial float order */
     int32_t reserved;
 } ppp_cfg;
 
@@ -147,7 +148,9 @@ int ppp_thin(const uint8_t* mask, const int32_t* sel, int64_t m,
              uint8_t* keep, void* scratch, void* stream);
 
 /* ---- step 5: patch graph (computePatchGraph.cu) ---------------------------
- * pairs u32 [n][6] = (z,y,x,z2,y2,x2); aff f32 [n]. */
+ * pairs u32 [n][6] = (z,y,x,z2,y2,x2); aff f32 [n].  Default: the terms are
+ * added into one float in the reference's loop order (the mutex watershed
+ * orders edges by |aff|); graph_flags bit2: parallel sum in double. */
 int ppp_patch_graph(const float* pred, const uint8_t* flags,
                     const int32_t* fgidx, const float* cons,
                     const uint32_t* pairs, int64_t n, const ppp_cfg* cfg,

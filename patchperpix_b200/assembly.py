@@ -236,13 +236,18 @@ class BlockAssembler:
         return arr
 
     # -- step 5 ------------------------------------------------------------
-    def patch_graph(self, pairs_dev):
-        """computePatchGraph_cuda (aff_patch_graph.py:113-187), matrix form."""
+    def patch_graph(self, pairs_dev, fast=None):
+        """computePatchGraph_cuda (aff_patch_graph.py:113-187), matrix form.
+        fast=True: parallel double-precision sum instead of the reference's
+        serial float order (kwargs ppp_graph_fast)."""
         torch = _torch()
         n = int(pairs_dev.shape[0])
         aff = torch.empty(max(n, 1), dtype=torch.float32, device=self.dev)
+        cfg = self.cfg
+        if fast is not None:
+            cfg = cc.make_cfg(self.shape, self.ps, **dict(self.kwargs, ppp_graph_fast=fast))
         cc.call('ppp_patch_graph', cc.ptr(self.pred), cc.ptr(self.flags), cc.ptr(self.fgidx),
-                cc.ptr(self.cons), cc.ptr(pairs_dev), n, self.cfg, cc.ptr(aff), self.stream)
+                cc.ptr(self.cons), cc.ptr(pairs_dev), n, cfg, cc.ptr(aff), self.stream)
         return aff[:n]
 
     # -- step 6 ------------------------------------------------------------

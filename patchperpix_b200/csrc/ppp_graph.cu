@@ -42,7 +42,7 @@ __device__ int pg_build_list(const Geo& g, const ppp_cfg& cfg, const float* __re
     const int64_t vc = ((int64_t)cz * g.Y + cy) * g.X + cx;
     if (threadIdx.x == 0) { s_scratch[16] = 0; s_scratch[17] = 0; }
     __syncthreads();
-    for (int base = 0; base < g.P; base += PG_THREADS) {
+    for (int base = 0; base < g.P; base += (int)blockDim.x) {
         int po = base + threadIdx.x;
         bool vote = false, inter = false;
         if (po < g.P) {
@@ -70,7 +70,7 @@ __device__ int pg_build_list(const Geo& g, const ppp_cfg& cfg, const float* __re
         __syncthreads();
         if (threadIdx.x == 0) {
             int t = 0, ti = 0;
-            for (int i = 0; i < PG_THREADS / 32; i++) { t += s_scratch[i]; ti += s_scratch[8 + i]; }
+            for (int i = 0; i < (int)blockDim.x / 32; i++) { t += s_scratch[i]; ti += s_scratch[8 + i]; }
             s_scratch[16] += t; s_scratch[17] += ti;
         }
         __syncthreads();
@@ -159,6 +159,215 @@ patch_graph_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ f
     }
 }
 
+// ---------------------------------------------------------------------------
+// reference-order patch affinity.  computePatchGraph.cu adds its up to P^2 terms
+// into ONE float, serially (po1 outer, po2 inner); like in rankPatches.cu the
+// rounding of that running sum is systematic (1e-3 relative at 41x41).  Only the
+// sign matters for the connected-components labelling, but the mutex watershed
+// (the flylight default) orders the edges by |aff|, so the default kernel
+// reproduces the exact sequence of float additions: the CTA (2 warps) produces
+// the terms of the flattened (i, j) sequence in chunks of PGR_CH into a double
+// buffer (skipped terms as 0.0f, which leaves a float sum unchanged) while
+// thread 0 adds the previous chunk in order.  The chain of ~n1*n2 dependent
+// FADDs of a pair bounds its latency; many light CTAs per SM run side by side.
+// ---------------------------------------------------------------------------
+#define PGR_THREADS 96          // warp 0 adds, warps 1-2 produce
+#define PGR_CH 256
+#define PGR_BIAS 512
+
+// ordered compaction of the voting pixels of patch (cz,cy,cx) (computePatchGraph.cu:41-52):
+// s_q = coordinates relative to (rz0,ry0,rx0), biased, packed z<<20|y<<10|x; s_row =
+// consensus row of the pixel; s_ii = rank among the pixels inside the other window, or -1
+__device__ int pgr_build_list(const Geo& g, const ppp_cfg& cfg, const float* __restrict__ pred,
+                              const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
+                              int cz, int cy, int cx, int oz, int oy, int ox,
+                              int rz0, int ry0, int rx0,
+                              int32_t* s_q, int32_t* s_row, int32_t* s_ii, int* s_scratch,
+                              int* n_inter)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = PGR_THREADS / 32;
+    const int64_t vc = ((int64_t)cz * g.Y + cy) * g.X + cx;
+    if (threadIdx.x == 0) { s_scratch[16] = 0; s_scratch[17] = 0; }
+    __syncthreads();
+    for (int base = 0; base < g.P; base += PGR_THREADS) {
+        int po = base + threadIdx.x;
+        bool vote = false, inter = false;
+        int q = 0, row = -1;
+        if (po < g.P) {
+            int qz, qy, qx;
+            po_decode(g, po, qz, qy, qx);
+            int z = cz + qz - g.rz, y = cy + qy - g.ry, x = cx + qx - g.rx;
+            if (z >= 0 && z < g.Z && y >= 0 && y < g.Y && x >= 0 && x < g.X) {
+                int pv = (z * g.Y + y) * g.X + x;
+                vote = (flags[pv] & PPP_FLAG_FG) && pred[(int64_t)po * g.V + vc] > cfg.th_gt;
+                inter = vote && abs(x - ox) <= g.rx && abs(y - oy) <= g.ry && abs(z - oz) <= g.rz;
+                if (vote) {
+                    row = fgidx[pv];
+                    q = ((z - rz0 + PGR_BIAS) << 20) | ((y - ry0 + PGR_BIAS) << 10) |
+                        (x - rx0 + PGR_BIAS);
+                }
+            }
+        }
+        unsigned bv = __ballot_sync(0xffffffffu, vote);
+        unsigned bi = __ballot_sync(0xffffffffu, inter);
+        if (lane == 0) { s_scratch[w] = __popc(bv); s_scratch[8 + w] = __popc(bi); }
+        __syncthreads();
+        int off = s_scratch[16], offi = s_scratch[17];
+        for (int i = 0; i < w; i++) { off += s_scratch[i]; offi += s_scratch[8 + i]; }
+        if (vote) {
+            unsigned lt = (1u << lane) - 1u;
+            int idx = off + __popc(bv & lt);
+            s_q[idx] = q;
+            s_row[idx] = row;
+            s_ii[idx] = inter ? offi + __popc(bi & lt) : -1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0, ti = 0;
+            for (int i = 0; i < nw; i++) { t += s_scratch[i]; ti += s_scratch[8 + i]; }
+            s_scratch[16] += t; s_scratch[17] += ti;
+        }
+        __syncthreads();
+    }
+    *n_inter = s_scratch[17];
+    return s_scratch[16];
+}
+
+__global__ void __launch_bounds__(PGR_THREADS)
+patch_graph_ref_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags,
+                       const int32_t* __restrict__ fgidx, const float* __restrict__ cons,
+                       const uint32_t* __restrict__ pairs, ppp_cfg cfg, float* __restrict__ aff)
+{
+    Geo g = make_geo(cfg);
+    extern __shared__ unsigned char smem_raw[];
+    int32_t* s_q1 = (int32_t*)smem_raw;           // [P] per list: packed coordinates,
+    int32_t* s_row1 = s_q1 + g.P;                 //     consensus row,
+    uint32_t* s_pw1 = (uint32_t*)(s_row1 + g.P);  //     LCG factor (0 = outside the intersection)
+    int32_t* s_q2 = (int32_t*)(s_pw1 + g.P);
+    int32_t* s_row2 = s_q2 + g.P;
+    uint32_t* s_pw2 = (uint32_t*)(s_row2 + g.P);
+    __shared__ int s_scr1[18], s_scr2[18];
+    __shared__ __align__(16) float s_val[2][PGR_CH];
+    __shared__ unsigned s_cnt[2];
+
+    const int64_t id = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int z1c = pairs[id * 6], y1c = pairs[id * 6 + 1], x1c = pairs[id * 6 + 2];
+    const int z2c = pairs[id * 6 + 3], y2c = pairs[id * 6 + 4], x2c = pairs[id * 6 + 5];
+    const uint32_t rnd0 = (uint32_t)z1c * (uint32_t)z2c * (uint32_t)y1c * (uint32_t)y2c *
+                          (uint32_t)x1c * (uint32_t)x2c;
+    // patches further apart than 2*ps on an axis share no slot: every term is skipped
+    // by the offset test (:98-101), sum and count stay 0
+    if (abs(z2c - z1c) > 2 * g.psz || abs(y2c - y1c) > 2 * g.psy || abs(x2c - x1c) > 2 * g.psx) {
+        if (tid == 0) aff[id] = 0.0f;
+        return;
+    }
+    int ni1, ni2;
+    const int n1 = pgr_build_list(g, cfg, pred, flags, fgidx, z1c, y1c, x1c, z2c, y2c, x2c,
+                                  z1c, y1c, x1c, s_q1, s_row1, (int32_t*)s_pw1, s_scr1, &ni1);
+    const int n2 = pgr_build_list(g, cfg, pred, flags, fgidx, z2c, y2c, x2c, z1c, y1c, x1c,
+                                  z1c, y1c, x1c, s_q2, s_row2, (int32_t*)s_pw2, s_scr2, &ni2);
+    const uint32_t a_n2 = pow_u32(LCG_A, (uint32_t)ni2);
+    // rank -> LCG factor, in place.  a is odd, so a^k is never 0: 0 marks "outside".
+    // k-th intersection pair (1-based) sees rnd0 * a^k, k = ii1 * ni2 + ii2 + 1
+    for (int i = tid; i < n1; i += PGR_THREADS) {
+        int ii = (int)s_pw1[i];
+        s_pw1[i] = ii >= 0 ? pow_u32(a_n2, (uint32_t)ii) : 0u;
+    }
+    for (int j = tid; j < n2; j += PGR_THREADS) {
+        int ii = (int)s_pw2[j];
+        s_pw2[j] = ii >= 0 ? pow_u32(LCG_A, (uint32_t)ii + 1u) : 0u;
+    }
+    __syncthreads();
+
+    const int total = n1 * n2;
+    const int nch = (total + PGR_CH - 1) / PGR_CH;
+    const int lane = tid & 31;
+    if (tid >= 32) {
+        // ---- producer warps: chunk c of the flattened (i, j) sequence -> s_val[c & 1] ----
+        const int pt = tid - 32;                  // 0..63
+        constexpr int TPT = PGR_CH / 64;          // terms per producer thread and chunk
+        unsigned cnt = 0;
+        int ic = 0, jc = 0;                       // (i, j) of the first term of the chunk
+        for (int c = 0; c < nch; c++) {
+            if (c >= 2) {                                         // buffer c&1 was consumed
+                if (c & 1) asm volatile("bar.sync 5, 96;\n" ::: "memory");
+                else asm volatile("bar.sync 4, 96;\n" ::: "memory");
+            }
+            float* dst = s_val[c & 1];
+            int64_t addr[TPT];
+#pragma unroll
+            for (int u = 0; u < TPT; u++) {
+                int i = ic, j = jc + pt + 64 * u;
+                while (j >= n2 && i < n1) { j -= n2; i++; }
+                addr[u] = -1;
+                if (i < n1) {
+                    const uint32_t w1 = s_pw1[i], w2 = s_pw2[j];
+                    bool skip = false;
+                    if (w1 != 0u && w2 != 0u) {                   // computePatchGraph.cu:75-86
+                        uint32_t rnd = rnd0 * w1 * w2;
+                        float rndT = (float)rnd / 4294967296.0f;
+                        skip = (double)rndT > 0.2;
+                    }
+                    const int a = s_q1[i], b = s_q2[j];
+                    int dz = (b >> 20) - (a >> 20), dy = ((b >> 10) & 1023) - ((a >> 10) & 1023),
+                        dx = (b & 1023) - (a & 1023);
+                    int rowb = s_row1[i];
+                    // raster index g1 <= g2  <=>  (dz,dy,dx) >= 0 lexicographically (:89-124)
+                    if (dz < 0 || (dz == 0 && (dy < 0 || (dy == 0 && dx < 0)))) {
+                        dz = -dz; dy = -dy; dx = -dx; rowb = s_row2[j];
+                    }
+                    // :98-101 / :116-119 (index = offset + ps - 1 in [0, 2ps))
+                    if (!skip && !(dz > g.psz || dy < -(g.psy - 1) || dy > g.psy ||
+                                   dx < -(g.psx - 1) || dx > g.psx)) {
+                        cnt++;
+                        const int k = k_of_offset(g, dz, dy, dx);
+                        if (k >= 0 && rowb >= 0) addr[u] = (int64_t)rowb * g.K + k;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < TPT; u++)
+                dst[pt + 64 * u] = addr[u] >= 0 ? cons[addr[u]] : 0.0f;
+            jc += PGR_CH;
+            while (jc >= n2 && ic < n1) { jc -= n2; ic++; }
+            __threadfence_block();
+            if (c & 1) asm volatile("bar.arrive 3, 96;\n" ::: "memory");     // chunk c is ready
+            else asm volatile("bar.arrive 2, 96;\n" ::: "memory");
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) s_cnt[(tid >> 5) - 1] = cnt;
+    } else {
+        // ---- adder warp: lane 0 adds the chunks in order ---------------------------------
+        float acc = 0.0f;
+        for (int c = 0; c < nch; c++) {
+            if (c & 1) asm volatile("bar.sync 3, 96;\n" ::: "memory");       // wait for chunk c
+            else asm volatile("bar.sync 2, 96;\n" ::: "memory");
+            if (lane == 0) {
+                const float4* v = (const float4*)s_val[c & 1];
+#pragma unroll 8
+                for (int q = 0; q < PGR_CH / 4; q++) {
+                    float4 t = v[q];
+                    acc += t.x; acc += t.y; acc += t.z; acc += t.w;
+                }
+            }
+            if (c + 2 < nch) {                                    // buffer free
+                __syncwarp();
+                if (c & 1) asm volatile("bar.arrive 5, 96;\n" ::: "memory");
+                else asm volatile("bar.arrive 4, 96;\n" ::: "memory");
+            }
+        }
+        __syncwarp();
+        if (lane == 0) s_val[0][0] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned c = s_cnt[0] + s_cnt[1];
+        const float acc = s_val[0][0];
+        aff[id] = (cfg.graph_flags & 1) ? acc / (float)(c > 1 ? c : 1) : acc;
+    }
+}
+
 extern "C" int ppp_patch_graph(const float* pred, const uint8_t* flags,
                                const int32_t* fgidx, const float* cons,
                                const uint32_t* pairs, int64_t n, const ppp_cfg* cfg,
@@ -167,6 +376,20 @@ extern "C" int ppp_patch_graph(const float* pred, const uint8_t* flags,
     if (n <= 0) return 0;
     Geo g = make_geo(*cfg);
     if (g.P > 32767) return ppp_fail(-1, "ppp_patch_graph: patch too large");
+    if (!(cfg->graph_flags & 4)) {                // default: the reference's summation order
+        if (g.psz > 128 || g.psy > 128 || g.psx > 128)
+            return ppp_fail(-1, "ppp_patch_graph: patch axis larger than 128");
+        size_t smem = (size_t)g.P * 24 + 16;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(patch_graph_ref_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem);
+            if (e != cudaSuccess) return ppp_fail((int)e, "ppp_patch_graph: smem attribute");
+        }
+        patch_graph_ref_kernel<<<(unsigned)n, PGR_THREADS, smem, (cudaStream_t)stream>>>(
+            pred, flags, fgidx, cons, pairs, *cfg, aff);
+        return ppp_check("ppp_patch_graph(reference order)");
+    }
     size_t smem = (size_t)g.P * 12 + 16;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(patch_graph_kernel,

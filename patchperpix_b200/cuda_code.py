@@ -94,7 +94,8 @@ def make_cfg(shape, patchshape, **kwargs):
     c.rank_flags = (1 if kwargs.get('rank_norm_patch_score', True) else 0) | \
                    (2 if kwargs.get('rank_int_counter', False) else 0) | \
                    (4 if kwargs.get('ppp_rank_fast', False) else 0)
-    c.graph_flags = 1 if kwargs.get('patch_graph_norm_aff', True) else 0
+    c.graph_flags = (1 if kwargs.get('patch_graph_norm_aff', True) else 0) | \
+                    (4 if kwargs.get('ppp_graph_fast', False) else 0)
     c.reserved = int(kwargs.get('ppp_tune', 0))
     return c
 
