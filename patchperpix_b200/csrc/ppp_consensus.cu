@@ -240,16 +240,21 @@ consensus_bits_kernel(const float* __restrict__ dp, const unsigned long long* __
 // summation order -> deterministic, and bit-identical to the simple kernel.
 // ---------------------------------------------------------------------------
 #define CT_T 8
+// consumer threads per CTA (+ one producer warp), centres per stage buffer; tuned on the
+// bench image together with CT_STAGES / CT_MINB below (two CTAs per SM)
 #ifndef CT_THREADS
-#define CT_THREADS 256
+#define CT_THREADS 192
 #endif
 #ifndef CT_NCCH
-#define CT_NCCH 64
+#define CT_NCCH 40
 #endif
 #define CT_XMAX 2048
 #define CT_MAXTILES 512
+#ifndef CT_MAXITEMS
 #define CT_MAXITEMS 6144
+#endif
 #define CT_MAXLINES 128
+#define CT_MAXSTAGES 8
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
 {
@@ -261,6 +266,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
     unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(a), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(a) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
 {
@@ -296,11 +306,12 @@ __device__ int ct_tiles_of_line(const uint8_t* __restrict__ flags, const int32_t
     const int ra = rows_before(fgidx, line_base, V, F);
     const int rb = rows_before(fgidx, line_base + X, V, F);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = CT_THREADS / 32;
+    const bool worker = threadIdx.x < CT_THREADS;      // the producer warp only keeps the barriers
     int ntot = 0;
     for (int base = ra; base < rb; base += CT_THREADS) {
         int r = base + threadIdx.x;
-        int v = r < rb ? rowvox[r] : 0;
-        bool ok = r < rb && (flags[v] & PPP_FLAG_GATED);
+        int v = (worker && r < rb) ? rowvox[r] : 0;
+        bool ok = worker && r < rb && (flags[v] & PPP_FLAG_GATED);
         unsigned bal = __ballot_sync(0xffffffffu, ok);
         if (lane == 0) s_scr[w] = __popc(bal);
         __syncthreads();
@@ -336,29 +347,33 @@ extern "C" int ppp_debug_ct_prof(unsigned long long* out, int reset)
 #define CT_TICK(i)
 #endif
 
+#ifndef CT_MINB
+#define CT_MINB 2
+#endif
 template <int NOY>
-__global__ void __launch_bounds__(CT_THREADS)
+__global__ void __launch_bounds__(CT_THREADS + 32, CT_MINB)
 consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
                       const int32_t* __restrict__ fgidx, const int32_t* __restrict__ rowvox,
                       int F, ppp_cfg cfg, const uint32_t* __restrict__ cnt,
-                      float* __restrict__ cons)
+                      float* __restrict__ cons, int S)
 {
     constexpr int T = CT_T;
     Geo g = make_geo(cfg);
     const int RS = g.rsg;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* sA = (float*)smem_raw;                                // [2][(1+NOY)][NCCH][RS]
+    float* sA = (float*)smem_raw;                                // [S][(1+NOY)][NCCH][RS]
     const int substride = CT_NCCH * RS;                          // one staged patch row
     const int bufstride = (1 + NOY) * substride;
-    int32_t* s_ra = (int32_t*)(sA + 2 * bufstride);              // [MAXLINES] first row per centre line
+    int32_t* s_ra = (int32_t*)(sA + S * bufstride);              // [MAXLINES] first row per centre line
     int32_t* s_rb = s_ra + CT_MAXLINES;                          // [MAXLINES]
     uint32_t* s_items = (uint32_t*)(s_rb + CT_MAXLINES);         // [MAXITEMS]
     int16_t* s_bt = (int16_t*)(s_items + CT_MAXITEMS);           // [MAXTILES] base tile starts
     int16_t* s_pt = s_bt + CT_MAXTILES;                          // [NOY][MAXTILES]
     int16_t* s_tmp = s_pt + NOY * CT_MAXTILES;                   // [XMAX]
-    __shared__ int s_scr[CT_THREADS / 32];
+    __shared__ int s_scr[CT_THREADS / 32 + 1];
     __shared__ int s_npt[NOY], s_nitems;
-    __shared__ __align__(8) uint64_t s_full[2];
+    __shared__ __align__(8) uint64_t s_full[CT_MAXSTAGES], s_empty[CT_MAXSTAGES];
+    __shared__ int2 s_info[CT_MAXSTAGES];                        // (centre line, centres) of a stage
 
     const int line = blockIdx.y;
     const int bz = line / g.Y, by = line % g.Y;
@@ -415,8 +430,10 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
             }
         }
         s_nitems = n;
-        mbar_init(&s_full[0], 1);
-        mbar_init(&s_full[1], 1);
+        for (int i = 0; i < S; i++) {
+            mbar_init(&s_full[i], 1);                             // the producer's expect_tx arrive
+            mbar_init(&s_empty[i], CT_THREADS / 32);              // one arrive per consumer warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     // ---- row ranges of the centre lines around the base line -------------------
@@ -432,10 +449,10 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
                     atomicAdd(&ct_prof[6], (unsigned long long)((nitems + CT_THREADS - 1) / CT_THREADS)); }
 #endif
     if (nitems == 0 || nlines <= 0) return;
-    unsigned phase0 = 0, phase1 = 0;
+    unsigned stage_no = 0;           // stages published (producer) / consumed (consumers) so far
 
     for (int ibase = 0; ibase < nitems; ibase += CT_THREADS) {
-        const bool have = ibase + tid < nitems;
+        const bool have = tid < CT_THREADS && ibase + tid < nitems;
         int my_t = 0, b0 = -30000, p0 = -30000;
         if (have) {
             uint32_t it = s_items[ibase + tid];
@@ -452,7 +469,7 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
         if (have && my_chi >= my_clo) { atomicMin(&s_clo, my_clo); atomicMax(&s_chi, my_chi); }
         __syncthreads();
         const int cxa = max(s_clo, g.rx), cxb = min(s_chi, g.X - 1 - g.rx);
-        for (int l = tid; l < nlines; l += CT_THREADS) {
+        for (int l = tid; l < nlines; l += CT_THREADS + 32) {
             int cz = cza + l / ncy, cy = cya + l % ncy;
             int64_t cline = ((int64_t)cz * g.Y + cy) * g.X;
             int ra = 0, rb = 0;
@@ -469,8 +486,10 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
 #pragma unroll
             for (int m = 0; m < T; m++) acc[j][m] = 0.0f;
 
-        // ---- software pipeline over (centre line, chunk) stages -----------------
-        int st_l = 0, st_c = s_ra[0];                 // next stage to issue
+        // ---- pipeline over (centre line, chunk) stages: a ring of S buffers, filled by
+        // the producer warp through the TMA engine (full barriers), released by the
+        // consumer warps one by one (empty barriers) — no CTA-wide barrier per stage, so
+        // warps whose tiles see no centre in a stage run ahead to the next ----------------
         // offset rows that have a patch row in centre line l (bit t), 0 = none
         auto act_mask = [&](int l) -> unsigned {
             int cz = cza + l / ncy, cy = cya + l % ncy;
@@ -483,87 +502,101 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
             }
             return m;
         };
-        // issue the TMA copies of the next non-empty stage into buffer `buf`
-        auto issue = [&](int buf, int& out_l) -> int {
-            while (st_l < nlines && !(act_mask(st_l) && st_c < s_rb[st_l])) {
-                st_l++;
-                if (st_l < nlines) st_c = s_ra[st_l];
-            }
-            out_l = st_l;
-            if (st_l >= nlines) return 0;
-            const int l = st_l, c0 = st_c;
-            const int nc = min(CT_NCCH, s_rb[l] - c0);
-            if (tid == 0) {
-                const unsigned am = act_mask(l);
-                const int cz = cza + l / ncy, cy = cya + l % ncy;
-                const int q1z = bz - cz + g.rz, q1y = by - cy + g.ry;
-                float* dst = sA + buf * bufstride;
-                const unsigned bytes = (unsigned)(nc * RS * 4);
-                mbar_expect_tx(&s_full[buf], (1 + __popc(am)) * bytes);
-                bulk_load(dst, dp + ((int64_t)(q1z * g.psy + q1y) * F + c0) * RS, bytes, &s_full[buf]);
-#pragma unroll
-                for (int t = 0; t < NOY; t++)
-                    if (am & (1u << t))
-                        bulk_load(dst + (1 + t) * substride,
-                                  dp + ((int64_t)((q1z + oz_t[t]) * g.psy + (q1y + oy_t[t])) * F + c0) * RS,
-                                  bytes, &s_full[buf]);
-            }
-            st_c += nc;
-            return nc;
-        };
-
-        int cur_l, nxt_l;
-        int cur_nc = issue(0, cur_l);
-        int buf = 0;
-        while (cur_nc > 0) {
-            int nxt_nc = issue(buf ^ 1, nxt_l);
-            if (buf == 0) { mbar_wait(&s_full[0], phase0); phase0 ^= 1; }
-            else { mbar_wait(&s_full[1], phase1); phase1 ^= 1; }
-            // ---- accumulate over the staged centres ---------------------------------
-            bool mine = have && my_chi >= my_clo && ((act_mask(cur_l) >> my_t) & 1u);
-            if (mine) {
-                const float* A1 = sA + buf * bufstride;
-                const int nc = cur_nc;
-                const int cx_first = __float_as_int(A1[0]);
-                const int cx_last = __float_as_int(A1[(nc - 1) * RS]);
-                if (!(cx_first > my_chi || cx_last < my_clo)) {
-                    int lo = 0, hi = nc;
-                    while (lo < hi) {
-                        int mid = (lo + hi) >> 1;
-                        if (__float_as_int(A1[mid * RS]) < my_clo) lo = mid + 1; else hi = mid;
+        if (tid >= CT_THREADS) {
+            if (tid == CT_THREADS) {
+                int st_l = 0, st_c = s_ra[0];
+                while (true) {
+                    while (st_l < nlines && !(act_mask(st_l) && st_c < s_rb[st_l])) {
+                        st_l++;
+                        if (st_l < nlines) st_c = s_ra[st_l];
                     }
-                    const float* A2 = A1 + (1 + my_t) * substride;
-                    for (int ci = lo; ci < nc; ci++) {
-                        const int cx = __float_as_int(A1[ci * RS]);
-                        if (cx > my_chi) break;
-                        const float* p1 = A1 + ci * RS + DP_GUARD + g.rx + (b0 - cx);
-                        const float* p2 = A2 + ci * RS + DP_GUARD + g.rx + (p0 - cx);
-                        // exactly one of the two products below is non-zero per pair:
-                        //   a1 * max(a2,0)          high-high (+) and background-high (-)
-                        //   max(a1,0) * min(a2,0)   high-background (-)
-                        // background-background pairs add exact zeros (they do not vote)
-                        float a1[T], h1[T], h2[T], l2[T];
-#pragma unroll
-                        for (int j = 0; j < T; j++) {
-                            a1[j] = p1[j];
-                            float a2 = p2[j];
-                            h1[j] = fmaxf(a1[j], 0.0f);
-                            h2[j] = fmaxf(a2, 0.0f);
-                            l2[j] = fminf(a2, 0.0f);
-                        }
-#pragma unroll
-                        for (int j = 0; j < T; j++)
-#pragma unroll
-                            for (int m = 0; m < T; m++)
-                                acc[j][m] = fmaf(h1[j], l2[m], fmaf(a1[j], h2[m], acc[j][m]));
+                    const int slot = (int)(stage_no % (unsigned)S);
+                    const unsigned use = stage_no / (unsigned)S;
+                    if (use > 0) mbar_wait(&s_empty[slot], (use - 1) & 1);
+                    stage_no++;
+                    if (st_l >= nlines) {                         // end of this batch
+                        s_info[slot] = make_int2(0, 0);
+                        mbar_arrive(&s_full[slot]);
+                        break;
                     }
+                    const int l = st_l, c0 = st_c;
+                    const int nc = min(CT_NCCH, s_rb[l] - c0);
+                    s_info[slot] = make_int2(l, nc);
+                    const unsigned am = act_mask(l);
+                    const int cz = cza + l / ncy, cy = cya + l % ncy;
+                    const int q1z = bz - cz + g.rz, q1y = by - cy + g.ry;
+                    float* dst = sA + slot * bufstride;
+                    const unsigned bytes = (unsigned)(nc * RS * 4);
+                    mbar_expect_tx(&s_full[slot], (1 + __popc(am)) * bytes);
+                    bulk_load(dst, dp + ((int64_t)(q1z * g.psy + q1y) * F + c0) * RS, bytes,
+                              &s_full[slot]);
+#pragma unroll
+                    for (int t = 0; t < NOY; t++)
+                        if (am & (1u << t))
+                            bulk_load(dst + (1 + t) * substride,
+                                      dp + ((int64_t)((q1z + oz_t[t]) * g.psy + (q1y + oy_t[t])) * F + c0) * RS,
+                                      bytes, &s_full[slot]);
+                    st_c += nc;
                 }
             }
-            __syncthreads();                      // buffer `buf` may be overwritten now
-            buf ^= 1;
-            cur_nc = nxt_nc;
-            cur_l = nxt_l;
+        } else {
+            while (true) {
+                const int slot = (int)(stage_no % (unsigned)S);
+                const unsigned use = stage_no / (unsigned)S;
+                mbar_wait(&s_full[slot], use & 1);
+                const int2 info = s_info[slot];
+                stage_no++;
+                const int cur_l = info.x, cur_nc = info.y;
+                // ---- accumulate over the staged centres ---------------------------------
+                bool mine = cur_nc > 0 && have && my_chi >= my_clo &&
+                            ((act_mask(cur_l) >> my_t) & 1u);
+                if (mine) {
+                    const float* A1 = sA + slot * bufstride;
+                    const int nc = cur_nc;
+                    const int cx_first = __float_as_int(A1[0]);
+                    const int cx_last = __float_as_int(A1[(nc - 1) * RS]);
+                    if (!(cx_first > my_chi || cx_last < my_clo)) {
+                        int lo = 0, hi = nc;
+                        while (lo < hi) {
+                            int mid = (lo + hi) >> 1;
+                            if (__float_as_int(A1[mid * RS]) < my_clo) lo = mid + 1; else hi = mid;
+                        }
+                        const float* A2 = A1 + (1 + my_t) * substride;
+                        for (int ci = lo; ci < nc; ci++) {
+                            const int cx = __float_as_int(A1[ci * RS]);
+                            if (cx > my_chi) break;
+                            const float* p1 = A1 + ci * RS + DP_GUARD + g.rx + (b0 - cx);
+                            const float* p2 = A2 + ci * RS + DP_GUARD + g.rx + (p0 - cx);
+                            // exactly one of the two products below is non-zero per pair:
+                            //   a1 * max(a2,0)          high-high (+) and background-high (-)
+                            //   max(a1,0) * min(a2,0)   high-background (-)
+                            // background-background pairs add exact zeros (they do not vote)
+                            float a1[T], h1[T], h2[T], l2[T];
+#pragma unroll
+                            for (int j = 0; j < T; j++) {
+                                a1[j] = p1[j];
+                                float a2 = p2[j];
+                                h1[j] = fmaxf(a1[j], 0.0f);
+                                h2[j] = fmaxf(a2, 0.0f);
+                                l2[j] = fminf(a2, 0.0f);
+                            }
+#pragma unroll
+                            for (int j = 0; j < T; j++)
+#pragma unroll
+                                for (int m = 0; m < T; m++)
+                                    acc[j][m] = fmaf(h1[j], l2[m], fmaf(a1[j], h2[m], acc[j][m]));
+                        }
+                    }
+                }
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&s_empty[slot]);  // this warp is done with the buffer
+                if (cur_nc == 0) break;
+            }
         }
+        // the producer's other lanes and every consumer agree on the stage count: the
+        // producer thread counted the same stages (one per buffer fill + the end marker)
+        stage_no = __shfl_sync(0xffffffffu, stage_no, 0);
+        __syncthreads();
         CT_TICK(1)
         // ---- epilogue: normalise with the integer counters and store -----------
         if (have) {
@@ -599,10 +632,20 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
 
 #define CT_NOY 3
 
-static size_t rows_smem(const Geo& g)
+static size_t rows_smem(const Geo& g, int stages)
 {
-    return (size_t)2 * (1 + CT_NOY) * CT_NCCH * g.rsg * 4 + 2 * CT_MAXLINES * 4 +
+    return (size_t)stages * (1 + CT_NOY) * CT_NCCH * g.rsg * 4 + 2 * CT_MAXLINES * 4 +
            (size_t)CT_MAXITEMS * 4 + (size_t)(1 + CT_NOY) * CT_MAXTILES * 2 + CT_XMAX * 2 + 128;
+}
+// ring depth: as many stage buffers as fit next to the static tables (2..CT_STAGES)
+#ifndef CT_STAGES
+#define CT_STAGES 2
+#endif
+static int rows_stages(const Geo& g)
+{
+    int s = CT_STAGES;
+    while (s > 2 && rows_smem(g, s) > 112 * 1024) s--;
+    return s;
 }
 
 extern "C" int64_t ppp_consensus_scratch_bytes(const ppp_cfg* cfg)
@@ -631,7 +674,19 @@ extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8
     if (g.X > CT_XMAX) return ppp_fail(-1, "ppp_consensus: X > 2048 unsupported, use blocks");
     if (g.psz * g.psy > CT_MAXLINES)
         return ppp_fail(-1, "ppp_consensus: more than 128 centre lines per window");
+    // worst-case work items of one CTA of the tiled kernel: base tiles x partner tiles
+    // within reach x offset rows; beyond the table the bit-guided gather takes over
+    {
+        const int nbt = (g.X + CT_T - 1) / CT_T;
+        int reach = (2 * (g.psx - 1) + 2 * CT_T - 1) / CT_T + 1;
+        if (reach > nbt) reach = nbt;
+        if ((int64_t)nbt * reach * CT_NOY > CT_MAXITEMS) {
+            if (impl == 3) return ppp_fail(-1, "ppp_consensus: line too long for the tiled kernel");
+            if (impl == 0) impl = 2;
+        }
+    }
     if (impl == 2 || (impl == 0 && g.psx < 16)) {
+        if (g.psx > 64) return ppp_fail(-1, "ppp_consensus: psx > 64 needs the tiled kernel");
         consensus_bits_kernel<<<(unsigned)F, 128, 0, s>>>(
             dp, (const unsigned long long*)rbits, flags, fgidx, rowvox, F, *cfg, cons, cnt);
         return ppp_check("ppp_consensus(bits)");
@@ -639,14 +694,15 @@ extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8
     consensus_count_kernel<<<(unsigned)F, 256, 0, s>>>(
         (const unsigned long long*)rbits, flags, fgidx, rowvox, *cfg, cons, cnt);
     if (cfg->prod_mode == 0) return ppp_check("ppp_consensus(count)");   // no float sums needed
-    size_t smem = rows_smem(g);
+    const int stages = rows_stages(g);
+    size_t smem = rows_smem(g, stages);
     cudaError_t e = cudaFuncSetAttribute(consensus_rows_kernel<CT_NOY>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return ppp_fail((int)e, "ppp_consensus: smem attribute");
     int nrows_off = (g.nz * g.ny - 1) / 2 + 1;
     // offset-row groups on x (scheduled first): the groups of one line share its A1 rows in L2
     dim3 grid((unsigned)((nrows_off + CT_NOY - 1) / CT_NOY), (unsigned)(g.Z * g.Y));
-    consensus_rows_kernel<CT_NOY><<<grid, CT_THREADS, smem, s>>>(
-        dp, flags, fgidx, rowvox, (int)F, *cfg, cnt, cons);
+    consensus_rows_kernel<CT_NOY><<<grid, CT_THREADS + 32, smem, s>>>(
+        dp, flags, fgidx, rowvox, (int)F, *cfg, cnt, cons, stages);
     return ppp_check("ppp_consensus(rows)");
 }
