@@ -8,11 +8,15 @@ A "step" = the whole assembly path (gate -> consensus -> rank -> cover ->
 thin -> patch graph -> CC -> paint) over one image.
 
   value : fg voxels / s, inputs resident in HBM, CUDA-event timed
-  e2e   : same through patchperpix_b200.vote_instances.to_instance_seg with
-          PINNED HOST inputs (H2D of the prediction + D2H of the labels inside
-          the timed region)
-  roofline : consensus kernel, algorithmic bytes P*4 + 1 + K*8 per fg voxel
-              / its CUDA-event time, vs MEASURED_PEAKS.json
+  e2e   : same through patchperpix_b200.vote_instances.to_instance_seg_stream
+          with PINNED HOST inputs (float16, the stored form): every step copies
+          its own prediction H2D and reads its labels back inside the timed
+          region; the copy of sample i+1 overlaps the assembly of sample i.
+          serial_ms_per_step = one to_instance_seg call after the other.
+  roofline : the stage with the largest CUDA-event time (consensus or rank),
+             algorithmic bytes per fg voxel (consensus
+             P*4 + 1 + K*8, rank P*4 + K*4 + 4) vs MEASURED_PEAKS.json;
+             roofline_other = the other one
   cpu_baseline : the reference kernels compiled for the host (oracle/_ref,
              all cores) + the oracle host logic on a bounded crop
 
@@ -225,7 +229,7 @@ def device_step(pred, fg, overlap, mask, ps, kw, timers=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -306,6 +310,7 @@ def main():
     numinst_h = torch.from_numpy(numinst).pin_memory()
     h2d = pred_h.numel() * 2 + fg_h.numel() * 2 + numinst_h.numel()
     d2h = fg_h.numel() * 2 + fg_h.numel()          # u16 labels + u8 foreground
+    # one sample after the other (what the reference's file loop does) ...
     for _ in range(2):
         vi.to_instance_seg(pred_h, fg_h, fg_h, numinst_h, ps, **KW)
     barrier()
@@ -313,14 +318,31 @@ def main():
     for _ in range(steps):
         inst_e2e, _ = vi.to_instance_seg(pred_h, fg_h, fg_h, numinst_h, ps, **KW)
     torch.cuda.synchronize()
+    e2e_serial_ms = (time.perf_counter() - te) * 1e3 / steps
+
+    # ... and through the multi-sample entry point, which uploads sample i+1 on a
+    # copy stream while sample i is assembled (every step still copies its own
+    # input from pinned memory inside the timed region and reads its labels back)
+    def feed(n):
+        for _ in range(n):
+            yield (pred_h, fg_h, fg_h, numinst_h)
+    for _ in vi.to_instance_seg_stream(feed(2), ps, **KW):
+        pass
+    barrier()
+    te = time.perf_counter()
+    for inst_s, _ in vi.to_instance_seg_stream(feed(steps), ps, **KW):
+        pass
+    torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - te) * 1e3 / steps
+    assert np.array_equal(inst_s, inst_e2e)
 
     # ---- max over ranks ------------------------------------------------------
     tot_fg = nfg
     if world > 1:
-        t = torch.tensor([ms, e2e_ms, cons_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms, cons_ms, rank_ms, e2e_serial_ms], device=dev,
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, cons_ms = (float(x) for x in t.tolist())
+        ms, e2e_ms, cons_ms, rank_ms, e2e_serial_ms = (float(x) for x in t.tolist())
         c = torch.tensor([nfg], device=dev, dtype=torch.int64)
         dist.all_reduce(c)
         tot_fg = int(c.item())
@@ -353,24 +375,30 @@ def main():
                     flags='flylight [vote_instances] defaults, mws=False'),
         e2e=dict(value=tot_fg / (e2e_ms * 1e-3) / 1e6, unit='Mvoxels/s',
                  h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                 ms_per_step=e2e_ms,
+                 ms_per_step=e2e_ms, api='vote_instances.to_instance_seg_stream',
+                 serial_ms_per_step=e2e_serial_ms,
                  input='float16 [P,Z,Y,X] pinned host buffer (the stored form), widened on the device'),
         gpu_launches=n_launch, clocks=clocks,
-        roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
-                      frac=achieved / peak, traffic=traffic.get('ppp_consensus'),
-                      kernel='ppp_consensus (consensus_count_kernel + consensus_rows_kernel)',
-                      kernel_ms=cons_ms, share_of_step=cons_ms / ms,
-                      bytes_per_fg_voxel=b_unit, peak_source=how,
-                      note='HBM is the bound SURVEY 8d assigns; the kernel itself is '
-                           'issue/latency-bound on ~1.8e10 pair visits (DESIGN.md section 6)'),
-        roofline_other=[dict(bound='hbm', kernel='ppp_rank (reference summation order)',
-                             kernel_ms=rank_ms, share_of_step=rank_ms / ms,
-                             bytes_per_fg_voxel=b_rank,
-                             achieved=b_rank * nfg / (rank_ms * 1e-3) / 1e9, peak=peak,
-                             unit='GB/s',
-                             frac=b_rank * nfg / (rank_ms * 1e-3) / 1e9 / peak,
-                             traffic=traffic.get('ppp_rank'))],
     )
+    r_cons = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
+                  frac=achieved / peak, traffic=traffic.get('ppp_consensus'),
+                  kernel='ppp_consensus (consensus_count_kernel + consensus_rows_kernel)',
+                  kernel_ms=cons_ms, share_of_step=cons_ms / ms,
+                  bytes_per_fg_voxel=b_unit, peak_source=how,
+                  note='HBM is the bound SURVEY 8d assigns; the kernel itself is '
+                       'issue/latency-bound on ~1.8e10 pair visits (DESIGN.md section 6)')
+    a_rank = b_rank * nfg / (rank_ms * 1e-3) / 1e9
+    r_rank = dict(bound='hbm', achieved=a_rank, peak=peak, unit='GB/s', frac=a_rank / peak,
+                  traffic=traffic.get('ppp_rank'),
+                  kernel='ppp_rank (rank_lists_kernel + sort + rank_ref_kernel, reference '
+                         'summation order)',
+                  kernel_ms=rank_ms, share_of_step=rank_ms / ms, bytes_per_fg_voxel=b_rank,
+                  peak_source=how,
+                  note='serial float order fixed by the reference; 4-byte gathers from a '
+                       'consensus array larger than L2 (DESIGN.md section 6)')
+    first, second = (r_cons, r_rank) if cons_ms >= rank_ms else (r_rank, r_cons)
+    line['roofline'] = first
+    line['roofline_other'] = [second]
     if not args.no_cpu_baseline:
         try:
             pn = pred.cpu().numpy()

@@ -189,6 +189,77 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
             _unpad(fg).cpu().numpy().astype(np.uint8))
 
 
+def to_instance_seg_stream(samples, patchshape, **kwargs):
+    """Assemble a sequence of samples, overlapping the host->device copy of the
+    next sample with the assembly of the current one (copy stream + events; the
+    reference handles samples strictly one after the other, run_ppp.py:1111-1190,
+    vote_instances.py:586-605).
+
+    samples: iterable of (pred_affs, foreground, mask_to_cover, numinst) host
+    arrays (numpy or pinned torch tensors; pred may be float16 as stored by the
+    predict step).  Yields what to_instance_seg returns, in order."""
+    import torch
+    dev = torch.device('cuda', torch.cuda.current_device())
+    main = torch.cuda.current_stream(dev)
+    copy = torch.cuda.Stream(dev)
+    bufs = [None, None]            # double-buffered device copies
+    free = [None, None]            # event: the buffer was consumed by the main stream
+
+    def as_tensor(a):
+        if isinstance(a, np.ndarray):
+            a = torch.from_numpy(np.ascontiguousarray(a))
+        return a.to(torch.uint8) if a.dtype == torch.bool else a
+
+    def upload(i, sample):
+        host = [as_tensor(a) for a in sample]
+        slot = i & 1
+        with torch.cuda.stream(copy):
+            if free[slot] is not None:
+                copy.wait_event(free[slot])
+            old = bufs[slot]
+            devt = []
+            for k, h in enumerate(host):
+                if old is not None and old[k].shape == h.shape and old[k].dtype == h.dtype:
+                    t = old[k]
+                else:
+                    t = torch.empty(h.shape, dtype=h.dtype, device=dev)
+                t.copy_(h, non_blocking=True)
+                devt.append(t)
+            ready = torch.cuda.Event()
+            ready.record(copy)
+        bufs[slot] = devt
+        return ready
+
+    it = iter(samples)
+    try:
+        nxt = next(it)
+    except StopIteration:
+        return
+    ready = upload(0, nxt)
+    i = 0
+    while nxt is not None:
+        cur_ready, slot = ready, i & 1
+        try:
+            nxt = next(it)
+            ready = upload(i + 1, nxt)                 # runs while sample i is assembled
+        except StopIteration:
+            nxt = None
+        main.wait_event(cur_ready)
+        pred, fg, mask, numinst = bufs[slot]
+        pred32 = pred.float() if pred.dtype != torch.float32 else pred
+        done = torch.cuda.Event()
+        done.record(main)                              # the f16 copy has been widened
+        if pred32 is not pred:
+            free[slot] = done
+        out = to_instance_seg(pred32, fg, mask, numinst, patchshape, **kwargs)
+        if pred32 is pred:
+            done = torch.cuda.Event()
+            done.record(main)
+            free[slot] = done
+        yield out
+        i += 1
+
+
 def do_block(block, foreground, mask, numinst, **kwargs):
     """vote_instances.py:455-483."""
     patchshape = kwargs['patchshape']

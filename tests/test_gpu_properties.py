@@ -285,3 +285,25 @@ def test_full_size_ranking_cover_thin_paint(full):
     # mutex watershed on the same graph: same painted support or smaller
     inst2, top = asm.label(pd, aff, thin, mws=True)
     assert bool(((inst2 > 0) <= inside).all()) and top >= 1
+
+
+def test_streamed_samples_equal_single_calls():
+    """to_instance_seg_stream (copy stream overlapping the next upload) returns
+    exactly what one to_instance_seg call per sample returns, in order, for
+    float16 and float32 inputs of different shapes."""
+    from patchperpix_b200 import vote_instances as vi
+    ps = np.array([1, 9, 9])
+    samples, want = [], []
+    for seed, shape, dt in ((201, (40, 56), np.float16), (202, (48, 48), np.float32),
+                            (203, (40, 56), np.float16)):
+        pred, numinst, _ = synth.make_case(kind='worms', patchshape=ps, seed=seed, shape=shape,
+                                           n_worms=3, width=(4, 6), length=(20, 40))
+        fg = pred[40] > np.float32(0.5)
+        samples.append((pred.astype(dt), fg, fg.copy(), numinst))
+        want.append(vi.to_instance_seg(pred.copy(), fg.copy(), fg.copy(), numinst.copy(),
+                                       ps.copy(), **FLY)[0])
+    got = [r[0] for r in vi.to_instance_seg_stream(iter(samples), ps, **FLY)]
+    assert len(got) == 3
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    assert list(vi.to_instance_seg_stream(iter([]), ps, **FLY)) == []
