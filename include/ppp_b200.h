@@ -132,7 +132,9 @@ int ppp_rank_sort(const float* score, const int32_t* cand, int64_t n,
  * mask u8 [V] (mask_to_cover, overlap already removed), overlap u8 [V] or NULL
  * (centres to skip, foreground_cover.py:144).  order[n] from ppp_rank_sort.
  * selected u8 [n] in/out (zero it before the first call).
- * pix_ths[n_pix]: the pixTh schedule (foreground_cover.py:35-39).
+ * pix_ths[n_pix] (device): the pixTh schedule (foreground_cover.py:35-39);
+ * NULL = the single threshold 0 of `select_patches_for_sparse_data`, computed
+ * without the serial walk (selected = first coverer of every mask voxel).
  * scratch: ppp_cover_scratch_bytes(cfg) bytes. */
 int64_t ppp_cover_scratch_bytes(const ppp_cfg* cfg);
 int ppp_cover(const uint8_t* mask, const uint8_t* overlap, const int32_t* order,

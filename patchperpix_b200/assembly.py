@@ -163,12 +163,16 @@ class BlockAssembler:
         n = int(order.numel())
         if n == 0:
             return order
-        if self.kwargs.get('select_patches_for_sparse_data', False):
-            pix = [0]
+        if self.kwargs.get('select_patches_for_sparse_data', False) and \
+                not self.kwargs.get('ppp_cover_serial', False):
+            pix, pix_t = [], None            # threshold 0 only: data-parallel form
         else:
-            mid = int(self.P / 2)
-            pix = [t for t in [500, 100, 50, 10, 0] if t < mid]
-        pix_t = torch.tensor(pix, dtype=torch.int32, device=self.dev)
+            if self.kwargs.get('select_patches_for_sparse_data', False):
+                pix = [0]
+            else:
+                mid = int(self.P / 2)
+                pix = [t for t in [500, 100, 50, 10, 0] if t < mid]
+            pix_t = torch.tensor(pix, dtype=torch.int32, device=self.dev)
         selected = torch.zeros(n, dtype=torch.uint8, device=self.dev)
         scratch = torch.empty(cc.call('ppp_cover_scratch_bytes', self.cfg),
                               dtype=torch.uint8, device=self.dev)

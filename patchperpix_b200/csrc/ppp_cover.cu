@@ -109,8 +109,49 @@ __device__ void bitvol_init(const Geo& g, const BitVol& bv, const uint8_t* __res
 extern "C" int64_t ppp_cover_scratch_bytes(const ppp_cfg* cfg)
 {
     Geo g = make_geo(*cfg);
-    return (int64_t)g.Z * g.Y * bitvol_wx(g.X) * 4 + 256;
+    int64_t bitvol = (int64_t)g.Z * g.Y * bitvol_wx(g.X) * 4;
+    int64_t first = g.V * 4 + 16;                 // minpos[V] + r* (threshold-0 path)
+    return (bitvol > first ? bitvol : first) + 256;
 }
+
+// One THREAD: still-uncovered voxels of the window of centre (cz,cy,cx) that the patch
+// bit string `pm` marks (no clearing).  Used where many candidates are counted side by
+// side: one candidate per thread keeps 1024 independent load chains in flight.
+__device__ __forceinline__ int patch_window_count_thread(const Geo& g, const BitVol& bv,
+                                                         const uint32_t* __restrict__ pm,
+                                                         int cz, int cy, int cx)
+{
+    int cnt = 0;
+    int bit = 0;
+    for (int qz = 0; qz < g.psz; qz++)
+        for (int qy = 0; qy < g.psy; qy++) {
+            const int r = (cz - g.rz + qz) * g.Y + (cy - g.ry + qy);
+            for (int j = 0; j < g.psx; j += 32) {
+                int nb = min(32, g.psx - j);
+                uint32_t keep = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+                uint32_t m = pm_get32(pm, g.W, bit + j) & keep;
+                if (m) cnt += __popc(m & bv_get32(bv, r, cx - g.rx + j));
+            }
+            bit += g.psx;
+        }
+    return cnt;
+}
+
+#ifdef COVER_PROFILE
+__device__ unsigned long long cover_prof[8];
+extern "C" int ppp_debug_cover_prof(unsigned long long* out, int reset)
+{
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(cover_prof, z, sizeof(z)); return 0; }
+    return (int)cudaMemcpyFromSymbol(out, cover_prof, 8 * sizeof(unsigned long long));
+}
+#define COVER_TICK_INIT long long t_prof = clock64();
+#define COVER_TICK(i) if (threadIdx.x == 0) { long long now_ = clock64(); cover_prof[i] += (unsigned long long)(now_ - t_prof); t_prof = now_; }
+#define COVER_COUNT(i, v) if (threadIdx.x == 0) cover_prof[i] += (unsigned long long)(v);
+#else
+#define COVER_TICK_INIT
+#define COVER_TICK(i)
+#define COVER_COUNT(i, v)
+#endif
 
 #define COVER_THREADS 1024
 #define THIN_THREADS 1024
@@ -143,18 +184,21 @@ cover_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ overl
     BitVol bv;
     bv.WX = bitvol_wx(g.X);
     bv.w = use_smem ? s_bits : gbits;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = COVER_THREADS / 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    COVER_TICK_INIT
     if (threadIdx.x == 0) s_remaining = 0;
     __syncthreads();
     bitvol_init(g, bv, mask, &s_remaining);
     __syncthreads();
+    COVER_TICK(0)
     for (int pi = 0; pi < n_pix; pi++) {
         const int pix_th = pix_ths[pi];
         for (int64_t r0 = 0; r0 < n; r0 += COVER_THREADS) {
             if (s_remaining <= 0) break;
-            // phase A: parallel upper bounds
-            for (int i = w; i < COVER_THREADS; i += nw) {
-                int64_t r = r0 + i;
+            COVER_COUNT(4, 1)
+            // phase A: parallel upper bounds, one candidate per thread
+            {
+                int64_t r = r0 + threadIdx.x;
                 int cnt = -1;
                 if (r < n && !selected[r]) {
                     int vc = order[r];
@@ -162,13 +206,14 @@ cover_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ overl
                     if (!(overlap != nullptr && overlap[vc]) && row >= 0) {   // :144
                         int cz, cy, cx;
                         vox_decode(g, vc, cz, cy, cx);
-                        cnt = patch_window_count<false>(g, bv, fcmask + (int64_t)row * g.W,
-                                                        cz, cy, cx, lane, nullptr);
+                        cnt = patch_window_count_thread(g, bv, fcmask + (int64_t)row * g.W,
+                                                        cz, cy, cx);
                     }
                 }
-                if (lane == 0) s_cnt[i] = cnt;
+                s_cnt[threadIdx.x] = cnt;
             }
             __syncthreads();
+            COVER_TICK(1)
             // phase B: replay of the survivors in rank order.  Sub-batches of up to 32
             // survivors: every warp stages the bit string of one survivor in shared
             // memory and re-counts it against the live mask in parallel; warp 0 then
@@ -188,6 +233,8 @@ cover_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ overl
             }
             __syncthreads();
             const int nsurv = s_nsurv;
+            COVER_TICK(2)
+            COVER_COUNT(5, nsurv)
             for (int sb = 0; sb < nsurv; sb += 32) {
                 if (s_remaining <= 0) break;
                 const int nb = min(32, nsurv - sb);
@@ -235,10 +282,99 @@ cover_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ overl
                     if (lane == 0) s_remaining = remaining;
                 }
                 __syncthreads();
+                COVER_COUNT(6, 1)
             }
+            COVER_TICK(3)
         }
         if (s_remaining < 1) break;                                  // :50-51
     }
+}
+
+// ---------------------------------------------------------------------------
+// greedy cover with pixel threshold 0 (`select_patches_for_sparse_data`, the
+// flylight default, foreground_cover.py:35-36) without the serial walk.
+// A candidate is selected iff at its turn some mask voxel under its patch is
+// still uncovered.  Let first(p) be the best-ranked (non-skipped) candidate whose
+// patch marks voxel p.  first(p) is always selected (nobody before it touches p),
+// and a selected candidate must be first(p) for the voxel that made it count
+// (an earlier coverer of p would itself have been selected and cleared p).  So
+//     selected = { first(p) : p in mask }  up to the position r* where the walk
+// stops: the last first(p) over the voxels inside the radslice (:128-129), or the
+// end of the list if one of them cannot be covered.  Four data-parallel passes.
+// ---------------------------------------------------------------------------
+__global__ void cover_first_init_kernel(int32_t* __restrict__ minpos, int64_t V, int32_t* rstar)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V) minpos[i] = 0x7fffffff;
+    if (i == 0) *rstar = -1;
+}
+
+__global__ void __launch_bounds__(256)
+cover_first_mark_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ overlap,
+                        const int32_t* __restrict__ order, int64_t n,
+                        const int32_t* __restrict__ fgidx, const uint32_t* __restrict__ fcmask,
+                        ppp_cfg cfg, int32_t* __restrict__ minpos)
+{
+    Geo g = make_geo(cfg);
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const int vc = order[r];
+    const int row = fgidx[vc];
+    if ((overlap != nullptr && overlap[vc]) || row < 0) return;             // :141-145
+    const uint32_t* pm = fcmask + (int64_t)row * g.W;
+    int cz, cy, cx;
+    vox_decode(g, vc, cz, cy, cx);
+    const int nrows = g.psz * g.psy;
+    for (int rr = lane; rr < nrows; rr += 32) {
+        int qz = rr / g.psy, qy = rr - qz * g.psy;
+        int z = cz - g.rz + qz, y = cy - g.ry + qy;
+        if (z < 0 || z >= g.Z || y < 0 || y >= g.Y) continue;
+        const int64_t line = ((int64_t)z * g.Y + y) * g.X;
+        for (int j = 0; j < g.psx; j += 32) {
+            int nb = min(32, g.psx - j);
+            uint32_t keep = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+            uint32_t m = pm_get32(pm, g.W, rr * g.psx + j) & keep;
+            while (m) {
+                int b = __ffs(m) - 1;
+                m &= m - 1;
+                int x = cx - g.rx + j + b;
+                if (x >= 0 && x < g.X && mask[line + x]) atomicMin(&minpos[line + x], (int)r);
+            }
+        }
+    }
+}
+
+// r* = where the reference's walk stops
+__global__ void cover_first_stop_kernel(const uint8_t* __restrict__ mask,
+                                        const int32_t* __restrict__ minpos, ppp_cfg cfg,
+                                        int64_t n, int32_t* rstar)
+{
+    Geo g = make_geo(cfg);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int v = -1;
+    if (i < g.V && mask[i]) {
+        int z, y, x;
+        vox_decode(g, (int)i, z, y, x);
+        if (z >= g.rz && z < g.Z - g.rz && y >= g.ry && y < g.Y - g.ry && x >= g.rx &&
+            x < g.X - g.rx) {
+            int mp = minpos[i];
+            v = mp == 0x7fffffff ? (int)(n - 1) : mp;
+        }
+    }
+    v = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v >= 0) atomicMax(rstar, v);
+}
+
+__global__ void cover_first_select_kernel(const uint8_t* __restrict__ mask,
+                                          const int32_t* __restrict__ minpos, int64_t V,
+                                          const int32_t* __restrict__ rstar,
+                                          uint8_t* __restrict__ selected)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V || !mask[i]) return;
+    int mp = minpos[i];
+    if (mp != 0x7fffffff && mp <= *rstar) selected[mp] = 1;
 }
 
 extern "C" int ppp_cover(const uint8_t* mask, const uint8_t* overlap, const int32_t* order,
@@ -248,6 +384,19 @@ extern "C" int ppp_cover(const uint8_t* mask, const uint8_t* overlap, const int3
 {
     if (n <= 0) return 0;
     Geo g = make_geo(*cfg);
+    if (pix_ths == nullptr) {
+        // pixel threshold 0 only (select_patches_for_sparse_data): data-parallel form
+        cudaStream_t st = (cudaStream_t)stream;
+        int32_t* minpos = (int32_t*)scratch;
+        int32_t* rstar = minpos + g.V;
+        const unsigned nb = (unsigned)((g.V + 255) / 256);
+        cover_first_init_kernel<<<nb, 256, 0, st>>>(minpos, g.V, rstar);
+        cover_first_mark_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(
+            mask, overlap, order, n, fgidx, fcmask, *cfg, minpos);
+        cover_first_stop_kernel<<<nb, 256, 0, st>>>(mask, minpos, *cfg, n, rstar);
+        cover_first_select_kernel<<<nb, 256, 0, st>>>(mask, minpos, g.V, rstar, selected);
+        return ppp_check("ppp_cover(first coverer)");
+    }
     size_t bytes = (size_t)g.Z * g.Y * bitvol_wx(g.X) * 4;
     int use_smem = bytes <= SMEM_BITVOL_MAX;
     size_t smem = (use_smem ? bytes : 0) + (size_t)32 * g.W * 4;

@@ -85,6 +85,11 @@ def test_rank_cover_thin_graph_labels(name):
     mask = torch.from_numpy((fg & ~(g['numinst'] > 1)).astype(np.uint8)).cuda()
     sel = asm.cover(mask, order)
     assert np.array_equal(asm.coords(sel), g['cover'])
+    # threshold 0 runs in the data-parallel "first coverer" form: the serial walk of
+    # the reference (kept for the dense threshold schedule) must select the same
+    asm.kwargs['ppp_cover_serial'] = True
+    assert torch.equal(asm.cover(mask, order), sel)
+    del asm.kwargs['ppp_cover_serial']
     thin = asm.thin(mask, sel) if not kw.get('skipThinCover', False) else sel
     assert np.array_equal(asm.coords(thin), g['thin'])
     pairs = asm.patch_pairs(asm.coords(thin))

@@ -239,6 +239,9 @@ def test_full_size_ranking_cover_thin_paint(full):
     assert bool((order[1:][tie] > order[:-1][tie]).all())         # ties keep raster order
     assert torch.equal(torch.sort(order)[0], torch.sort(cand)[0])  # a permutation
     sel = asm.cover(mask, order)
+    asm.kwargs['ppp_cover_serial'] = True                          # the serial walk agrees
+    assert torch.equal(asm.cover(mask, order), sel)
+    del asm.kwargs['ppp_cover_serial']
     thin = asm.thin(mask, sel)
     assert set(thin.tolist()) <= set(sel.tolist()) <= set(order.tolist())
     fc = np.float32(full['kw']['fc_threshold'])
