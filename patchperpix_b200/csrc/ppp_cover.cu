@@ -505,9 +505,298 @@ thin_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__ sel, i
     }
 }
 
+// ---------------------------------------------------------------------------
+// greedy set cover in ROUNDS instead of one selection per step.
+//
+// The reference picks the patch with the largest remaining set (first maximum),
+// removes its voxels from every other set, and repeats until nothing inside the
+// radslice is left (foreground_cover.py:196-254).  Observations:
+//  * counts only fall, and only for patches whose window intersects the chosen
+//    one ("neighbours");
+//  * hence the counts at selection time are non-increasing along the serial
+//    run, i.e. the serial order of the selected patches is exactly their order
+//    by (count at selection, descending; index, ascending);
+//  * a patch that currently beats all its live neighbours in that order (a
+//    LOCAL maximum) is selected by the serial run before any of its neighbours,
+//    with exactly its current count, provided the run gets that far: nobody who
+//    could lower its count can become the global maximum before it.
+// So all local maxima of a round are selected at once (their windows are
+// pairwise disjoint), their neighbours are re-counted, and the only thing that
+// needs the serial order is WHERE the run stops: the first position of the
+// (count, index)-sorted selection at which the voxels newly removed from the
+// radslice add up to its initial content.  Rounds continue until no live patch
+// could still sort before that position; later selections are dropped.
+// One CTA; per-patch state in global scratch (L1/L2), bit volume as before.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool thin_better(int ca, int ia, int cb, int ib)
+{
+    return ca > cb || (ca == cb && ia < ib);       // a is chosen before b
+}
+
+// like patch_window_count<true>, but safe when several warps clear disjoint
+// windows that may share 32-bit words of the bit volume
+__device__ __forceinline__ int patch_window_clear_atomic(const Geo& g, const BitVol& bv,
+                                                         const uint32_t* __restrict__ pm,
+                                                         int cz, int cy, int cx, int lane)
+{
+    int rad = 0;
+    const int nrows = g.psz * g.psy;
+    for (int rr = lane; rr < nrows; rr += 32) {
+        int qz = rr / g.psy, qy = rr - qz * g.psy;
+        int z = cz - g.rz + qz, y = cy - g.ry + qy;
+        int r = z * g.Y + y;
+        bool row_in_rad = z >= g.rz && z < g.Z - g.rz && y >= g.ry && y < g.Y - g.ry;
+        for (int j = 0; j < g.psx; j += 32) {
+            int nb = min(32, g.psx - j);
+            uint32_t keep = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+            int x0 = cx - g.rx + j;
+            uint32_t m = bv_get32(bv, r, x0) & pm_get32(pm, g.W, rr * g.psx + j) & keep;
+            if (m) {
+                const int wi = x0 >> 5, sft = x0 & 31;
+                uint32_t* p = bv.w + (int64_t)r * bv.WX + wi;
+                atomicAnd(p, ~(m << sft));
+                if (sft && wi + 1 < bv.WX) atomicAnd(p + 1, ~(m >> (32 - sft)));
+                if (row_in_rad) rad += __popc(m & rad_xmask(g, x0, nb));
+            }
+        }
+    }
+    return warp_sum_i(rad);
+}
+
+#define THIN_LIST 2048      // per-round lists kept in shared memory
+#define THIN_DEG 64         // neighbour-list budget per patch (average); beyond: brute force
+
+__global__ void __launch_bounds__(THIN_THREADS)
+thin_rounds_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__ sel, int64_t m64,
+                   const int32_t* __restrict__ fgidx, const uint32_t* __restrict__ fcmask,
+                   ppp_cfg cfg, uint8_t* __restrict__ keep, uint32_t* gbits, int32_t* gstate,
+                   int use_smem)
+{
+    Geo g = make_geo(cfg);
+    extern __shared__ uint32_t s_bits[];
+    __shared__ int s_remaining, s_total, s_nnew, s_nrec, s_go, s_cutc, s_cuti, s_nsel, s_lists;
+    __shared__ int s_new[THIN_LIST];               // patches selected in this round
+    __shared__ int s_rec[THIN_LIST];               // patches to count again / selected so far
+    __shared__ int s_scan[THIN_THREADS / 32];
+    const int m = (int)m64;
+    // per-patch state (global scratch): count, packed centre, fcmask row, count at
+    // selection (-1: not selected), voxels newly removed from the radslice, round of
+    // selection, neighbour list (patches whose window intersects) as offsets + entries
+    int32_t* cnt = gstate;
+    int32_t* ctr = cnt + m;
+    int32_t* row = ctr + m;
+    int32_t* csel = row + m;
+    int32_t* rcl = csel + m;
+    int32_t* rnd = rcl + m;
+    int32_t* off = rnd + m;                        // [m + 1]
+    int32_t* nbr = off + m + 1;                    // [<= THIN_DEG * m]
+    BitVol bv;
+    bv.WX = bitvol_wx(g.X);
+    bv.w = use_smem ? s_bits : gbits;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = THIN_THREADS / 32;
+    if (tid == 0) { s_remaining = 0; s_cutc = -1; s_cuti = -1; }
+    __syncthreads();
+    bitvol_init(g, bv, mask, &s_remaining);
+    for (int i = tid; i < m; i += THIN_THREADS) {
+        int vc = sel[i], z, y, x;
+        vox_decode(g, vc, z, y, x);
+        ctr[i] = (z << 22) | (y << 11) | x;
+        row[i] = fgidx[vc];
+        csel[i] = -1;
+        rcl[i] = 0;
+        rnd[i] = -1;
+        keep[i] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) s_total = s_remaining;
+    // initial |S_i|
+    for (int i = w; i < m; i += nw) {
+        int c = ctr[i], rw = row[i], n = 0;
+        if (rw >= 0)
+            n = patch_window_count<false>(g, bv, fcmask + (int64_t)rw * g.W, c >> 22,
+                                          (c >> 11) & 2047, c & 2047, lane, nullptr);
+        if (lane == 0) cnt[i] = n;
+    }
+    auto overlap = [&](int a, int b) {
+        return abs((a >> 22) - (b >> 22)) < g.psz &&
+               abs(((a >> 11) & 2047) - ((b >> 11) & 2047)) < g.psy &&
+               abs((a & 2047) - (b & 2047)) < g.psx;
+    };
+    // ---- neighbour lists (once): degree, exclusive scan, fill --------------------------
+    int carry = 0;
+    for (int base = 0; base < m; base += THIN_THREADS) {
+        const int i = base + tid;
+        int d = 0;
+        if (i < m) {
+            const int pi = ctr[i];
+            for (int j = 0; j < m; j++) d += (j != i && overlap(pi, ctr[j])) ? 1 : 0;
+        }
+        int incl = d;                              // block-wide exclusive scan of d
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_scan[w] = incl;
+        __syncthreads();
+        int wbase = 0, tot = 0;
+        for (int q = 0; q < nw; q++) { if (q < w) wbase += s_scan[q]; tot += s_scan[q]; }
+        if (i < m) off[i] = carry + wbase + incl - d;
+        carry += tot;
+        __syncthreads();
+    }
+    if (tid == 0) { off[m] = carry; s_lists = carry <= THIN_DEG * m; }
+    __syncthreads();
+    const bool lists = s_lists != 0;
+    if (lists)
+        for (int i = tid; i < m; i += THIN_THREADS) {
+            const int pi = ctr[i];
+            int o = off[i];
+            for (int j = 0; j < m; j++)
+                if (j != i && overlap(pi, ctr[j])) nbr[o++] = j;
+        }
+    __syncthreads();
+    int round = 0;
+    while (true) {
+        // ---- 1. local maxima among the live patches ----------------------------------
+        if (tid == 0) { s_nnew = 0; s_nrec = 0; s_go = 0; }
+        __syncthreads();
+        for (int i = tid; i < m; i += THIN_THREADS) {
+            const int ci = cnt[i];
+            if (ci <= 0 || csel[i] >= 0) continue;
+            bool lm = true;
+            if (lists) {
+                for (int q = off[i], e = off[i + 1]; q < e && lm; q++) {
+                    const int j = nbr[q], cj = cnt[j];
+                    if (cj > 0 && csel[j] < 0 && thin_better(cj, j, ci, i)) lm = false;
+                }
+            } else {
+                const int pi = ctr[i];
+                for (int j = 0; j < m && lm; j++) {
+                    const int cj = cnt[j];
+                    if (cj > 0 && j != i && csel[j] < 0 && thin_better(cj, j, ci, i) &&
+                        overlap(pi, ctr[j]))
+                        lm = false;
+                }
+            }
+            if (lm) {
+                int k = atomicAdd(&s_nnew, 1);
+                if (k < THIN_LIST) s_new[k] = i;
+            }
+        }
+        __syncthreads();
+        const int nnew = min(s_nnew, THIN_LIST);   // overflow: the rest is taken next round
+        if (nnew == 0) break;                      // nothing left that covers anything
+        // ---- 2. select them: windows are pairwise disjoint ----------------------------
+        for (int k = w; k < nnew; k += nw) {
+            const int i = s_new[k], c = ctr[i];
+            int rc = patch_window_clear_atomic(g, bv, fcmask + (int64_t)row[i] * g.W, c >> 22,
+                                               (c >> 11) & 2047, c & 2047, lane);
+            if (lane == 0) {
+                csel[i] = cnt[i]; rcl[i] = rc; rnd[i] = round;
+                atomicSub(&s_remaining, rc);
+            }
+        }
+        __syncthreads();
+        // ---- 3. count their live neighbours again --------------------------------------
+        for (int i = tid; i < m; i += THIN_THREADS) {
+            if (cnt[i] <= 0 || csel[i] >= 0) continue;
+            bool hit = false;
+            if (lists) {
+                for (int q = off[i], e = off[i + 1]; q < e && !hit; q++) hit = rnd[nbr[q]] == round;
+            } else {
+                const int pi = ctr[i];
+                for (int k = 0; k < nnew && !hit; k++) hit = overlap(pi, ctr[s_new[k]]);
+            }
+            if (hit) {
+                int k = atomicAdd(&s_nrec, 1);
+                if (k < THIN_LIST) s_rec[k] = i;
+                else s_go = 2;                     // list overflow: count everything (below)
+            }
+        }
+        __syncthreads();
+        if (s_go == 2) {
+            for (int i = w; i < m; i += nw) {
+                if (cnt[i] <= 0 || csel[i] >= 0) continue;
+                int c = ctr[i];
+                int n = patch_window_count<false>(g, bv, fcmask + (int64_t)row[i] * g.W, c >> 22,
+                                                  (c >> 11) & 2047, c & 2047, lane, nullptr);
+                if (lane == 0) cnt[i] = n;
+            }
+        } else {
+            const int nrec = s_nrec;
+            for (int k = w; k < nrec; k += nw) {
+                const int i = s_rec[k], c = ctr[i];
+                int n = patch_window_count<false>(g, bv, fcmask + (int64_t)row[i] * g.W, c >> 22,
+                                                  (c >> 11) & 2047, c & 2047, lane, nullptr);
+                if (lane == 0) cnt[i] = n;
+            }
+        }
+        round++;
+        __syncthreads();
+        // ---- 4. can the run already be cut? ---------------------------------------------
+        if (s_remaining > 0) continue;             // the radslice is not empty yet
+        // position where the serial run stops: first patch (in selection order) at which
+        // the removed radslice voxels add up to the initial content.  The selected
+        // patches are gathered into shared memory first (s_rec is free here).
+        if (tid == 0) { s_cutc = -1; s_cuti = 0x7fffffff; s_go = 0; s_nsel = 0; }
+        __syncthreads();
+        for (int i = tid; i < m; i += THIN_THREADS)
+            if (csel[i] >= 0) {
+                int k = atomicAdd(&s_nsel, 1);
+                if (k < THIN_LIST) s_rec[k] = i;
+            }
+        __syncthreads();
+        const int total = s_total;
+        const int nsel = s_nsel;
+        const bool gathered = nsel <= THIN_LIST;
+        auto removed_upto = [&](int i, int ci) {   // voxels removed up to and including i
+            int acc = 0;
+            if (gathered) {
+                for (int k = 0; k < nsel; k++) {
+                    const int j = s_rec[k], cj = csel[j];
+                    if (j == i || thin_better(cj, j, ci, i)) acc += rcl[j];
+                }
+            } else {
+                for (int j = 0; j < m; j++) {
+                    const int cj = csel[j];
+                    if (cj >= 0 && (j == i || thin_better(cj, j, ci, i))) acc += rcl[j];
+                }
+            }
+            return acc;
+        };
+        const int nloop = gathered ? nsel : m;
+        for (int k = tid; k < nloop; k += THIN_THREADS) {
+            const int i = gathered ? s_rec[k] : k, ci = csel[i];
+            if (ci >= 0 && removed_upto(i, ci) >= total) atomicMax(&s_cutc, ci);
+        }
+        __syncthreads();
+        const int cutc = s_cutc;                   // count of the patch at the cut
+        for (int k = tid; k < nloop; k += THIN_THREADS) {
+            const int i = gathered ? s_rec[k] : k, ci = csel[i];
+            if (ci == cutc && removed_upto(i, ci) >= total) atomicMin(&s_cuti, i);
+        }
+        __syncthreads();
+        const int cuti = s_cuti;
+        // a live patch that could still be selected before the cut keeps the rounds going
+        for (int i = tid; i < m; i += THIN_THREADS)
+            if (cnt[i] > 0 && csel[i] < 0 && thin_better(cnt[i], i, cutc, cuti)) s_go = 1;
+        __syncthreads();
+        if (s_go == 0) break;
+    }
+    __syncthreads();
+    // ---- result: the selection up to the cut (everything if the radslice never emptied) --
+    const bool cut = s_remaining <= 0 && s_cutc >= 0;
+    const int cutc = s_cutc, cuti = s_cuti;
+    for (int i = tid; i < m; i += THIN_THREADS) {
+        const int ci = csel[i];
+        keep[i] = (ci >= 0 && (!cut || (i == cuti) || thin_better(ci, i, cutc, cuti))) ? 1 : 0;
+    }
+}
+
 extern "C" int64_t ppp_thin_scratch_bytes(const ppp_cfg* cfg, int64_t m)
 {
-    return ppp_cover_scratch_bytes(cfg) + 256 + 4 * (m > 0 ? m : 0);
+    // bit volume + per-patch state (6 ints + offset) + neighbour lists (THIN_DEG per patch)
+    return ppp_cover_scratch_bytes(cfg) + 512 + (28 + 4 * THIN_DEG) * (m > 0 ? m : 0);
 }
 
 extern "C" int ppp_thin(const uint8_t* mask, const int32_t* sel, int64_t m,
@@ -525,9 +814,21 @@ extern "C" int ppp_thin(const uint8_t* mask, const int32_t* sel, int64_t m,
                                              SMEM_BITVOL_MAX);
         if (e != cudaSuccess) return ppp_fail((int)e, "ppp_thin: smem attribute");
     }
-    // scratch: [bit volume][counts m]
+    // scratch: [bit volume][per-patch state 5 x m]
     uint32_t* gbits = (uint32_t*)scratch;
     int32_t* gcounts = (int32_t*)((char*)scratch + ((bytes + 255) / 256) * 256);
+    if (!(cfg->reserved & 0x10000) && g.Z < 512 && g.Y < 2048 && g.X < 2048 &&
+        m < 0x7fffffff / 8) {
+        if (use_smem) {
+            cudaError_t e = cudaFuncSetAttribute(thin_rounds_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 SMEM_BITVOL_MAX);
+            if (e != cudaSuccess) return ppp_fail((int)e, "ppp_thin: smem attribute");
+        }
+        thin_rounds_kernel<<<1, THIN_THREADS, smem, (cudaStream_t)stream>>>(
+            mask, sel, m, fgidx, fcmask, *cfg, keep, gbits, gcounts, use_smem);
+        return ppp_check("ppp_thin(rounds)");
+    }
     thin_kernel<<<1, THIN_THREADS, smem, (cudaStream_t)stream>>>(
         mask, sel, m, fgidx, fcmask, *cfg, keep, gbits, gcounts, use_smem);
     return ppp_check("ppp_thin");

@@ -92,6 +92,13 @@ def test_rank_cover_thin_graph_labels(name):
     del asm.kwargs['ppp_cover_serial']
     thin = asm.thin(mask, sel) if not kw.get('skipThinCover', False) else sel
     assert np.array_equal(asm.coords(thin), g['thin'])
+    if not kw.get('skipThinCover', False):
+        # rounds of local maxima (default) == one selection per step (ppp_tune bit 16)
+        from patchperpix_b200 import cuda_code as cc
+        cfg0 = asm.cfg
+        asm.cfg = cc.make_cfg(asm.shape, asm.ps, **dict(asm.kwargs, ppp_tune=0x10000))
+        assert torch.equal(asm.thin(mask, sel), thin)
+        asm.cfg = cfg0
     pairs = asm.patch_pairs(asm.coords(thin))
     assert np.array_equal(pairs, g['pairs'])
     pd = torch.from_numpy(pairs.view(np.int32)).cuda()

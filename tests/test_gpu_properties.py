@@ -243,6 +243,13 @@ def test_full_size_ranking_cover_thin_paint(full):
     assert torch.equal(asm.cover(mask, order), sel)
     del asm.kwargs['ppp_cover_serial']
     thin = asm.thin(mask, sel)
+    # thinning runs in rounds of local maxima; the one-selection-per-step form of the
+    # reference (ppp_tune bit 16) must keep exactly the same patches
+    from patchperpix_b200 import cuda_code as cc
+    cfg0 = asm.cfg
+    asm.cfg = cc.make_cfg(asm.shape, asm.ps, **dict(asm.kwargs, ppp_tune=0x10000))
+    assert torch.equal(asm.thin(mask, sel), thin)
+    asm.cfg = cfg0
     assert set(thin.tolist()) <= set(sel.tolist()) <= set(order.tolist())
     fc = np.float32(full['kw']['fc_threshold'])
     ry, rx = int(ps[1]) // 2, int(ps[2]) // 2
