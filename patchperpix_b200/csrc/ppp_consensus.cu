@@ -101,42 +101,79 @@ consensus_count_kernel(const unsigned long long* __restrict__ rbits,
                        float* __restrict__ cons, uint32_t* __restrict__ cnt)
 {
     Geo g = make_geo(cfg);
+    extern __shared__ __align__(16) unsigned char cc_smem[];
+    const int nrw = g.psz * g.psy;
+    unsigned long long* s_rb = (unsigned long long*)cc_smem;     // [nrw][2] bits of this row
+    int32_t* s_prow = (int32_t*)(s_rb + 2 * nrw);                // [K] partner row of a live slot
+    uint16_t* s_k = (uint16_t*)(s_prow + g.K);                   // [K] its slot index
+    __shared__ int s_n;
     const int64_t row = blockIdx.x;
     const int vb = rowvox[row];
     int bz, by, bx;
     vox_decode(g, vb, bz, by, bx);
     const bool gated = (flags[vb] & PPP_FLAG_GATED) != 0;
-    const int nrw = g.psz * g.psy;
     const unsigned long long* rb = rbits + row * nrw * 2;
-    for (int k = threadIdx.x; k < g.K; k += blockDim.x) {
-        uint32_t outc = 0;
+    for (int i = threadIdx.x; i < 2 * nrw; i += blockDim.x) s_rb[i] = rb[i];
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    // pass 1: slots whose partner is gated are compacted (dense warps in pass 2), all
+    // others are written as zeros right away
+    const int lane = threadIdx.x & 31;
+    for (int k0 = 0; k0 < g.K; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        int prow = -1;
+        if (k < g.K && gated) {
+            int lin = k + g.K + 1;
+            int ox = lin % g.nx - (g.psx - 1);
+            int t = lin / g.nx;
+            int oy = t % g.ny - (g.psy - 1);
+            int oz = t / g.ny - (g.psz - 1);
+            int pz = bz + oz, py = by + oy, px = bx + ox;
+            if (pz >= 0 && pz < g.Z && py >= 0 && py < g.Y && px >= 0 && px < g.X) {
+                int vp = (pz * g.Y + py) * g.X + px;
+                if (flags[vp] & PPP_FLAG_GATED) prow = fgidx[vp];
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, prow >= 0);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_n, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (prow >= 0) {
+            int idx = base + __popc(bal & ((1u << lane) - 1u));
+            s_prow[idx] = prow;
+            s_k[idx] = (uint16_t)k;
+        } else if (k < g.K) {
+            cnt[row * g.K + k] = 0;
+            cons[row * g.K + k] = 0.0f;
+        }
+    }
+    __syncthreads();
+    // pass 2: counters of the live slots
+    const int n = s_n;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int k = s_k[idx];
+        const unsigned long long* rp = rbits + (int64_t)s_prow[idx] * nrw * 2;
         int lin = k + g.K + 1;
         int ox = lin % g.nx - (g.psx - 1);
         int t = lin / g.nx;
         int oy = t % g.ny - (g.psy - 1);
         int oz = t / g.ny - (g.psz - 1);
-        int pz = bz + oz, py = by + oy, px = bx + ox;
-        if (gated && pz >= 0 && pz < g.Z && py >= 0 && py < g.Y && px >= 0 && px < g.X) {
-            int vp = (pz * g.Y + py) * g.X + px;
-            if (flags[vp] & PPP_FLAG_GATED) {
-                const unsigned long long* rp = rbits + (int64_t)fgidx[vp] * nrw * 2;
-                int pos = 0, neg = 0;
-                // centre offsets d (from b) with d - o inside the partner's window
-                int dz0 = max(-g.rz, oz - g.rz), dz1 = min(g.rz, oz + g.rz);
-                int dy0 = max(-g.ry, oy - g.ry), dy1 = min(g.ry, oy + g.ry);
-                for (int dz = dz0; dz <= dz1; dz++)
-                for (int dy = dy0; dy <= dy1; dy++) {
-                    int w1 = (dz + g.rz) * g.psy + (dy + g.ry);
-                    int w2 = (dz - oz + g.rz) * g.psy + (dy - oy + g.ry);
-                    unsigned long long h1 = rb[2 * w1], l1 = rb[2 * w1 + 1];
-                    unsigned long long h2 = rp[2 * w2], l2 = rp[2 * w2 + 1];
-                    if (ox >= 0) { h2 <<= ox; l2 <<= ox; } else { h2 >>= -ox; l2 >>= -ox; }
-                    pos += __popcll(h1 & h2);
-                    neg += __popcll(h1 & l2) + __popcll(l1 & h2);
-                }
-                outc = ((uint32_t)neg << 16) | (uint32_t)pos;
-            }
+        int pos = 0, neg = 0;
+        // centre offsets d (from b) with d - o inside the partner's window
+        int dz0 = max(-g.rz, oz - g.rz), dz1 = min(g.rz, oz + g.rz);
+        int dy0 = max(-g.ry, oy - g.ry), dy1 = min(g.ry, oy + g.ry);
+        for (int dz = dz0; dz <= dz1; dz++)
+        for (int dy = dy0; dy <= dy1; dy++) {
+            int w1 = (dz + g.rz) * g.psy + (dy + g.ry);
+            int w2 = (dz - oz + g.rz) * g.psy + (dy - oy + g.ry);
+            unsigned long long h1 = s_rb[2 * w1], l1 = s_rb[2 * w1 + 1];
+            const ulonglong2 hl = *(const ulonglong2*)(rp + 2 * w2);
+            unsigned long long h2 = hl.x, l2 = hl.y;
+            if (ox >= 0) { h2 <<= ox; l2 <<= ox; } else { h2 >>= -ox; l2 >>= -ox; }
+            pos += __popcll(h1 & h2);
+            neg += __popcll(h1 & l2) + __popcll(l1 & h2);
         }
+        const uint32_t outc = ((uint32_t)neg << 16) | (uint32_t)pos;
         cnt[row * g.K + k] = outc;
         // plain vote counter (no probability product): the counters are the result
         cons[row * g.K + k] = (cfg.prod_mode == 0 && outc)
@@ -691,8 +728,16 @@ extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8
             dp, (const unsigned long long*)rbits, flags, fgidx, rowvox, F, *cfg, cons, cnt);
         return ppp_check("ppp_consensus(bits)");
     }
-    consensus_count_kernel<<<(unsigned)F, 256, 0, s>>>(
-        (const unsigned long long*)rbits, flags, fgidx, rowvox, *cfg, cons, cnt);
+    {
+        if (g.K > 65535) return ppp_fail(-1, "ppp_consensus: more than 65535 offsets");
+        size_t csm = (size_t)g.psz * g.psy * 16 + (size_t)g.K * 6 + 16;
+        cudaError_t ce = cudaFuncSetAttribute(consensus_count_kernel,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)csm);
+        if (ce != cudaSuccess) return ppp_fail((int)ce, "ppp_consensus: smem attribute (count)");
+        consensus_count_kernel<<<(unsigned)F, 256, csm, s>>>(
+            (const unsigned long long*)rbits, flags, fgidx, rowvox, *cfg, cons, cnt);
+    }
     if (cfg->prod_mode == 0) return ppp_check("ppp_consensus(count)");   // no float sums needed
     const int stages = rows_stages(g);
     size_t smem = rows_smem(g, stages);

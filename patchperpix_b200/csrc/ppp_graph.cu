@@ -219,7 +219,7 @@ __device__ int pgr_build_list(const Geo& g, const ppp_cfg& cfg, const float* __r
             int idx = off + __popc(bv & lt);
             s_q[idx] = q;
             s_row[idx] = row;
-            s_ii[idx] = inter ? offi + __popc(bi & lt) : -1;
+            if (s_ii != nullptr) s_ii[idx] = inter ? offi + __popc(bi & lt) : -1;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -233,6 +233,9 @@ __device__ int pgr_build_list(const Geo& g, const ppp_cfg& cfg, const float* __r
     return s_scratch[16];
 }
 
+// LCG = false: every pair has a zero coordinate product (2-D data, z = 0): the sub-sampling
+// state stays 0 and nothing is ever skipped, so the factor tables are not needed
+template <bool LCG>
 __global__ void __launch_bounds__(PGR_THREADS)
 patch_graph_ref_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags,
                        const int32_t* __restrict__ fgidx, const float* __restrict__ cons,
@@ -242,10 +245,10 @@ patch_graph_ref_kernel(const float* __restrict__ pred, const uint8_t* __restrict
     extern __shared__ unsigned char smem_raw[];
     int32_t* s_q1 = (int32_t*)smem_raw;           // [P] per list: packed coordinates,
     int32_t* s_row1 = s_q1 + g.P;                 //     consensus row,
-    uint32_t* s_pw1 = (uint32_t*)(s_row1 + g.P);  //     LCG factor (0 = outside the intersection)
-    int32_t* s_q2 = (int32_t*)(s_pw1 + g.P);
+    int32_t* s_q2 = s_row1 + g.P;
     int32_t* s_row2 = s_q2 + g.P;
-    uint32_t* s_pw2 = (uint32_t*)(s_row2 + g.P);
+    uint32_t* s_pw1 = (uint32_t*)(s_row2 + g.P);  //     LCG factor (0 = outside the intersection)
+    uint32_t* s_pw2 = s_pw1 + g.P;                //     (only with LCG)
     __shared__ int s_scr1[18], s_scr2[18];
     __shared__ __align__(16) float s_val[2][PGR_CH];
     __shared__ unsigned s_cnt[2];
@@ -264,19 +267,23 @@ patch_graph_ref_kernel(const float* __restrict__ pred, const uint8_t* __restrict
     }
     int ni1, ni2;
     const int n1 = pgr_build_list(g, cfg, pred, flags, fgidx, z1c, y1c, x1c, z2c, y2c, x2c,
-                                  z1c, y1c, x1c, s_q1, s_row1, (int32_t*)s_pw1, s_scr1, &ni1);
+                                  z1c, y1c, x1c, s_q1, s_row1, LCG ? (int32_t*)s_pw1 : nullptr,
+                                  s_scr1, &ni1);
     const int n2 = pgr_build_list(g, cfg, pred, flags, fgidx, z2c, y2c, x2c, z1c, y1c, x1c,
-                                  z1c, y1c, x1c, s_q2, s_row2, (int32_t*)s_pw2, s_scr2, &ni2);
-    const uint32_t a_n2 = pow_u32(LCG_A, (uint32_t)ni2);
-    // rank -> LCG factor, in place.  a is odd, so a^k is never 0: 0 marks "outside".
-    // k-th intersection pair (1-based) sees rnd0 * a^k, k = ii1 * ni2 + ii2 + 1
-    for (int i = tid; i < n1; i += PGR_THREADS) {
-        int ii = (int)s_pw1[i];
-        s_pw1[i] = ii >= 0 ? pow_u32(a_n2, (uint32_t)ii) : 0u;
-    }
-    for (int j = tid; j < n2; j += PGR_THREADS) {
-        int ii = (int)s_pw2[j];
-        s_pw2[j] = ii >= 0 ? pow_u32(LCG_A, (uint32_t)ii + 1u) : 0u;
+                                  z1c, y1c, x1c, s_q2, s_row2, LCG ? (int32_t*)s_pw2 : nullptr,
+                                  s_scr2, &ni2);
+    if (LCG) {
+        const uint32_t a_n2 = pow_u32(LCG_A, (uint32_t)ni2);
+        // rank -> LCG factor, in place.  a is odd, so a^k is never 0: 0 marks "outside".
+        // k-th intersection pair (1-based) sees rnd0 * a^k, k = ii1 * ni2 + ii2 + 1
+        for (int i = tid; i < n1; i += PGR_THREADS) {
+            int ii = (int)s_pw1[i];
+            s_pw1[i] = ii >= 0 ? pow_u32(a_n2, (uint32_t)ii) : 0u;
+        }
+        for (int j = tid; j < n2; j += PGR_THREADS) {
+            int ii = (int)s_pw2[j];
+            s_pw2[j] = ii >= 0 ? pow_u32(LCG_A, (uint32_t)ii + 1u) : 0u;
+        }
     }
     __syncthreads();
 
@@ -302,12 +309,14 @@ patch_graph_ref_kernel(const float* __restrict__ pred, const uint8_t* __restrict
                 while (j >= n2 && i < n1) { j -= n2; i++; }
                 addr[u] = -1;
                 if (i < n1) {
-                    const uint32_t w1 = s_pw1[i], w2 = s_pw2[j];
                     bool skip = false;
-                    if (w1 != 0u && w2 != 0u) {                   // computePatchGraph.cu:75-86
-                        uint32_t rnd = rnd0 * w1 * w2;
-                        float rndT = (float)rnd / 4294967296.0f;
-                        skip = (double)rndT > 0.2;
+                    if (LCG) {
+                        const uint32_t w1 = s_pw1[i], w2 = s_pw2[j];
+                        if (w1 != 0u && w2 != 0u) {               // computePatchGraph.cu:75-86
+                            uint32_t rnd = rnd0 * w1 * w2;
+                            float rndT = (float)rnd / 4294967296.0f;
+                            skip = (double)rndT > 0.2;
+                        }
                     }
                     const int a = s_q1[i], b = s_q2[j];
                     int dz = (b >> 20) - (a >> 20), dy = ((b >> 10) & 1023) - ((a >> 10) & 1023),
@@ -379,15 +388,22 @@ extern "C" int ppp_patch_graph(const float* pred, const uint8_t* flags,
     if (!(cfg->graph_flags & 4)) {                // default: the reference's summation order
         if (g.psz > 128 || g.psy > 128 || g.psx > 128)
             return ppp_fail(-1, "ppp_patch_graph: patch axis larger than 128");
-        size_t smem = (size_t)g.P * 24 + 16;
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(patch_graph_ref_kernel,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem);
-            if (e != cudaSuccess) return ppp_fail((int)e, "ppp_patch_graph: smem attribute");
-        }
-        patch_graph_ref_kernel<<<(unsigned)n, PGR_THREADS, smem, (cudaStream_t)stream>>>(
-            pred, flags, fgidx, cons, pairs, *cfg, aff);
+        // rnd0 = z*z2*y*y2*x*x2 (computePatchGraph.cu:24-27) is 0 for every pair of a
+        // single-slice volume: no sub-sampling, no factor tables
+        const bool lcg = g.Z > 1;
+        size_t smem = (size_t)g.P * (lcg ? 24 : 16) + 16;
+        cudaError_t e = lcg
+            ? cudaFuncSetAttribute(patch_graph_ref_kernel<true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+            : cudaFuncSetAttribute(patch_graph_ref_kernel<false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return ppp_fail((int)e, "ppp_patch_graph: smem attribute");
+        if (lcg)
+            patch_graph_ref_kernel<true><<<(unsigned)n, PGR_THREADS, smem, (cudaStream_t)stream>>>(
+                pred, flags, fgidx, cons, pairs, *cfg, aff);
+        else
+            patch_graph_ref_kernel<false><<<(unsigned)n, PGR_THREADS, smem, (cudaStream_t)stream>>>(
+                pred, flags, fgidx, cons, pairs, *cfg, aff);
         return ppp_check("ppp_patch_graph(reference order)");
     }
     size_t smem = (size_t)g.P * 12 + 16;
