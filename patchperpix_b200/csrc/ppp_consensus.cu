@@ -667,7 +667,9 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
     }
 }
 
+#ifndef CT_NOY
 #define CT_NOY 3
+#endif
 
 static size_t rows_smem(const Geo& g, int stages)
 {
