@@ -335,6 +335,8 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - te) * 1e3 / steps
     assert np.array_equal(inst_s, inst_e2e)
+    sys.stderr.write('[bench] rank %d: step %.2f ms  consensus %.2f  rank %.2f  e2e serial %.2f  '
+                     'e2e streamed %.2f ms\n' % (rank, ms, cons_ms, rank_ms, e2e_serial_ms, e2e_ms))
 
     # ---- max over ranks ------------------------------------------------------
     tot_fg = nfg

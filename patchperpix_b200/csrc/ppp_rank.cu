@@ -449,6 +449,7 @@ extern "C" int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fg
     {                                                                                       \
         int64_t ngroups = (F + CPW - 1) / CPW;                                              \
         int64_t nblk = (ngroups + RR_WARPS - 1) / RR_WARPS;                                 \
+        if (grid_cap > 0 && nblk > grid_cap) nblk = grid_cap;                               \
         if (idx32)                                                                          \
             rank_ref_kernel<CPW, B, T, int32_t><<<(unsigned)nblk, RR_WARPS * 32, 0, s>>>(   \
                 rowvox, cons, e_lin, (int64_t)(lb / 2), x_row, meta, perm, F, *cfg, score); \
@@ -456,6 +457,8 @@ extern "C" int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fg
             rank_ref_kernel<CPW, B, T, int64_t><<<(unsigned)nblk, RR_WARPS * 32, 0, s>>>(   \
                 rowvox, cons, e_lin, (int64_t)(lb / 2), x_row, meta, perm, F, *cfg, score); \
     }
+    // tuning: resident CTAs per SM (0 = one CTA per group of centres, no grid-stride)
+    const int64_t grid_cap = (int64_t)((cfg->reserved >> 12) & 15) * 148;
     switch ((cfg->reserved >> 8) & 7) {
     case 1: RR_LAUNCH(4, 4, 2); break;
     case 2: RR_LAUNCH(4, 2, 2); break;
