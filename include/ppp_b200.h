@@ -174,7 +174,8 @@ int ppp_label_cc(const uint32_t* pairs, const float* aff, int64_t n,
  * node_vox / node_label i32 [<= 2n] out: voxel index and component id of every
  * graph node in insertion order; id 0 = the node joined nothing and is not
  * painted.  Ids equal the reference's instance values (merged-away ids leave
- * gaps).  *n_nodes, *n_labels (= largest id) out.  Scatter node_label into
+ * gaps).  *n_nodes, *n_labels out; n_labels = ids ever created = length of the
+ * reference's component list (the largest surviving label may be smaller).  Scatter node_label into
  * comp[node_vox] and paint with ppp_paint / ppp_paint_patches. */
 int ppp_mws_host(const uint32_t* pairs, const float* aff, int64_t n,
                  const ppp_cfg* cfg, int32_t* node_vox, int32_t* node_label,
@@ -186,6 +187,12 @@ int ppp_mws_host(const uint32_t* pairs, const float* aff, int64_t n,
 int ppp_paint(const float* pred, const int32_t* nodes, int64_t m,
               const int32_t* comp, const ppp_cfg* cfg, int32_t* instances,
               void* stream);
+
+/* `one_instance_per_channel` (graph_to_labeling.py:57-95): instances i32
+ * [n_comp][V] (zeroed by the caller), channel c-1 = component c painted alone. */
+int ppp_paint_channels(const float* pred, const int32_t* nodes, int64_t m,
+                       const int32_t* comp, const ppp_cfg* cfg, int32_t* instances,
+                       void* stream);
 
 /* same with the member patches as a compact f32 [m][P] array (blockwise path:
  * only the selected patches of a volume that does not fit the device are read,

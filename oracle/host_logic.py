@@ -182,8 +182,10 @@ def mutex_watershed(g):
 
 
 def label_instances(pairs, aff, pred, patchshape, rad, shape, patch_threshold,
-                    dtype=np.uint16, mws=False):
-    """aff_patch_graph.py:31-40 + graph_to_labeling.py:44-84."""
+                    dtype=np.uint16, mws=False, per_channel=False):
+    """aff_patch_graph.py:31-40 + graph_to_labeling.py:44-84; per_channel =
+    one_instance_per_channel (:57-95, 114-115): every component painted into its
+    own volume, stacked."""
     g = nx.Graph()
     for i, a in enumerate(aff):
         if a != 0:
@@ -194,15 +196,20 @@ def label_instances(pairs, aff, pred, patchshape, rad, shape, patch_threshold,
         if a > 0:
             pos.add_edge(e0, e1, weight=a)
     inst = np.zeros(shape, dtype)
-    comps = []
+    comps, channels = [], []
     ccs = mutex_watershed(g) if mws else nx.connected_components(pos)
     for k, cc in enumerate(ccs):
         comps.append(sorted(cc))
+        target = np.zeros(shape, dtype) if per_channel else inst
         for idx in cc:
             idx = np.array(idx)
             patch = pred[(slice(None),) + tuple(idx)].reshape(patchshape)
             sl = _window(idx, rad)
-            inst[sl][patch > patch_threshold] = k + 1
+            target[sl][patch > patch_threshold] = k + 1
+        if per_channel:
+            channels.append(target)
+    if per_channel:
+        inst = np.stack(channels, axis=0) if channels else np.zeros((0,) + tuple(shape), dtype)
     return inst, comps
 
 
@@ -239,7 +246,8 @@ def assemble(pred, foreground, numinst, patchshape, kw, kern):
     out['aff'] = aff
     inst, comps = label_instances(pairs, aff, pred, ps, rad, foreground.shape,
                                   np.float32(kw['patch_threshold']),
-                                  mws=kw.get('mws', False))
+                                  mws=kw.get('mws', False),
+                                  per_channel=kw.get('one_instance_per_channel', False))
     out['instances'] = inst
     out['components'] = comps
     return out

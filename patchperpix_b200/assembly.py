@@ -24,7 +24,7 @@ def mutex_watershed(pairs, aff, cfg):
     aff_patch_graph.py:31-40) through ppp_mws_host: the one serial graph pass of
     the path, host side like the pair search.  pairs u32 [n,6], aff f32 [n]
     (numpy); cfg carries the volume shape.  Returns (node_vox i32 [m],
-    node_label i32 [m], largest label); label 0 = node joined nothing."""
+    node_label i32 [m], number of component ids created); label 0 = node joined nothing."""
     import ctypes
     pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 6)
     aff = np.ascontiguousarray(aff, np.float32)
@@ -255,11 +255,12 @@ class BlockAssembler:
         return aff[:n]
 
     # -- step 6 ------------------------------------------------------------
-    def label(self, pairs_dev, aff, nodes, pred=None, cfg=None, mws=False):
+    def label(self, pairs_dev, aff, nodes, pred=None, cfg=None, mws=False, per_channel=False):
         """setAffgraph + affGraphToInstances (aff_patch_graph.py:31-40,
         graph_to_labeling.py:44-84).  Returns (instances i32 [Z,Y,X], n_comp).
         mws: partition by mutex watershed (graph_mws.py) instead of the
-        components over aff > 0."""
+        components over aff > 0.  per_channel: one channel per component
+        (`one_instance_per_channel`), instances i32 [n_comp,Z,Y,X]."""
         torch = _torch()
         cfg = cfg or self.cfg
         pred = self.pred if pred is None else pred
@@ -271,18 +272,25 @@ class BlockAssembler:
             comp = torch.zeros(V, dtype=torch.int32, device=self.dev)
             nodes = torch.from_numpy(node_vox).to(self.dev)
             comp[nodes.long()] = torch.from_numpy(node_label).to(self.dev)
-            inst = torch.zeros(self.shape, dtype=torch.int32, device=self.dev)
-            cc.call('ppp_paint', cc.ptr(pred), cc.ptr(nodes), int(nodes.numel()), cc.ptr(comp),
-                    cfg, cc.ptr(inst), self.stream)
-            return inst, top
+            return self._paint(pred, nodes, comp, cfg, top, per_channel), top
         comp = torch.empty(V, dtype=torch.int32, device=self.dev)
         ncomp = torch.zeros(1, dtype=torch.int32, device=self.dev)
         scratch = torch.empty(cc.call('ppp_label_scratch_bytes', V, n), dtype=torch.uint8,
                               device=self.dev)
         cc.call('ppp_label_cc', cc.ptr(pairs_dev), cc.ptr(aff), n, cfg, cc.ptr(comp),
                 cc.ptr(ncomp), cc.ptr(scratch), self.stream)
+        n_comp = int(ncomp.item())
+        return self._paint(pred, nodes.contiguous(), comp, cfg, n_comp, per_channel), n_comp
+
+    def _paint(self, pred, nodes, comp, cfg, n_comp, per_channel):
+        torch = _torch()
+        if per_channel:
+            inst = torch.zeros((n_comp,) + self.shape, dtype=torch.int32, device=self.dev)
+            if n_comp > 0:
+                cc.call('ppp_paint_channels', cc.ptr(pred), cc.ptr(nodes), int(nodes.numel()),
+                        cc.ptr(comp), cfg, cc.ptr(inst), self.stream)
+            return inst
         inst = torch.zeros(self.shape, dtype=torch.int32, device=self.dev)
-        nodes = nodes.contiguous()
         cc.call('ppp_paint', cc.ptr(pred), cc.ptr(nodes), int(nodes.numel()), cc.ptr(comp),
                 cfg, cc.ptr(inst), self.stream)
-        return inst, int(ncomp.item())
+        return inst

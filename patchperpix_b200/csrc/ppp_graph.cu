@@ -635,6 +635,39 @@ extern "C" int ppp_paint(const float* pred, const int32_t* nodes, int64_t m,
     return ppp_check("ppp_paint");
 }
 
+// one channel per component (`one_instance_per_channel`, graph_to_labeling.py:57-95):
+// channel c-1 of instances [n_comp][V] holds component c painted alone
+__global__ void paint_channels_kernel(const float* __restrict__ pred,
+                                      const int32_t* __restrict__ nodes,
+                                      const int32_t* __restrict__ comp, ppp_cfg cfg,
+                                      int32_t* __restrict__ instances)
+{
+    Geo g = make_geo(cfg);
+    const int vc = nodes[blockIdx.x];
+    const int c = comp[vc];
+    if (c <= 0) return;
+    int cz, cy, cx;
+    vox_decode(g, vc, cz, cy, cx);
+    int32_t* chan = instances + (int64_t)(c - 1) * g.V;
+    for (int po = threadIdx.x; po < g.P; po += blockDim.x) {
+        int qz, qy, qx;
+        po_decode(g, po, qz, qy, qx);
+        int z = cz + qz - g.rz, y = cy + qy - g.ry, x = cx + qx - g.rx;
+        if (z < 0 || z >= g.Z || y < 0 || y >= g.Y || x < 0 || x >= g.X) continue;
+        if (pred[(int64_t)po * g.V + vc] > cfg.pt_gt) chan[(z * g.Y + y) * g.X + x] = c;
+    }
+}
+
+extern "C" int ppp_paint_channels(const float* pred, const int32_t* nodes, int64_t m,
+                                  const int32_t* comp, const ppp_cfg* cfg, int32_t* instances,
+                                  void* stream)
+{
+    if (m <= 0) return 0;
+    paint_channels_kernel<<<(unsigned)m, 128, 0, (cudaStream_t)stream>>>(pred, nodes, comp, *cfg,
+                                                                          instances);
+    return ppp_check("ppp_paint_channels");
+}
+
 // same, with the member patches handed over as a compact [m][P] array (the
 // blockwise path reads only the selected patches of a volume that does not fit
 // the device, stitch_patch_graph.py:380-385)

@@ -140,13 +140,13 @@ extern "C" int ppp_mws_host(const uint32_t* pairs, const float* aff, int64_t n,
             while (max_id > 0 && members[max_id] == 0) max_id--;
         }
     }
-    int top = 0;
     for (int i = 0; i < nn; i++) {
         node_vox[i] = (int32_t)vox[i];
         node_label[i] = cid[cl.find(i)];
-        top = std::max(top, node_label[i]);
     }
     *n_nodes = nn;
-    *n_labels = top;
+    // ids ever created = length of the reference's component list (graph_mws.py:78-81);
+    // ids merged away stay in it as empty components
+    *n_labels = (int32_t)members.size() - 1;
     return 0;
 }

@@ -25,8 +25,7 @@ logger = logging.getLogger(__name__)
 
 _UNSUPPORTED = ('isbiHack', 'debug', 'graphToInst', 'use_score_oracle',
                 'mark_close_neighboorhood', 'select_patches_overlap_neighborhood',
-                'thin_cover_use_kd', 'one_instance_per_channel',
-                'no_overlap_per_channel', 'shuffle_patches')
+                'thin_cover_use_kd', 'no_overlap_per_channel', 'shuffle_patches')
 
 
 def merge_dicts(sink, source):
@@ -181,10 +180,15 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
         (pairs[:, 0].astype(np.int64) * Y + pairs[:, 1]) * X + pairs[:, 2],
         (pairs[:, 3].astype(np.int64) * Y + pairs[:, 4]) * X + pairs[:, 5]]))
     nodes = torch.from_numpy(nodes_np.astype(np.int32)).to(pred.device)
-    inst, ncomp = asm.label(pairs_dev, aff, nodes, mws=kwargs.get('mws', False))
+    per_channel = bool(kwargs.get('one_instance_per_channel', False))
+    inst, ncomp = asm.label(pairs_dev, aff, nodes, mws=kwargs.get('mws', False),
+                            per_channel=per_channel)
     if ncomp > 65535:
         logger.warning("%d components do not fit the reference's uint16 labels", ncomp)
-    inst = _unpad(inst)
+    if per_channel:                                            # graph_to_labeling.py:143-151
+        inst = inst[(slice(None),) + radslice] if kwargs.get("pad_with_ps", False) else inst
+    else:
+        inst = _unpad(inst)
     return (inst.cpu().numpy().astype(np.uint16),
             _unpad(fg).cpu().numpy().astype(np.uint8))
 
@@ -299,7 +303,10 @@ def do_all(aff_file, patchshape=np.array([1, 25, 25]), **kwargs):
         return
     foreground = foreground.astype(np.uint8)
     if kwargs.get('crop_to_foreground', True):                 # :535-540
-        instances[foreground == 0] = 0
+        if kwargs.get('one_instance_per_channel', False):
+            instances[:, foreground == 0] = 0
+        else:
+            instances[foreground == 0] = 0
     fn = os.path.splitext(os.path.basename(aff_file))[0]
     from .io_util import write_result
     write_result(os.path.join(kwargs['result_folder'], fn),

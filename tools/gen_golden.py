@@ -271,6 +271,20 @@ def run_mws(S):
         res['inst/' + name] = inst
         print('mws %-24s inst=%d (cc: %d)' % (name, len(np.unique(inst)) - 1,
                                              len(np.unique(g['instances'])) - 1))
+        # one_instance_per_channel (graph_to_labeling.py:57-95), both partitions; the
+        # stack is stored as (channel of every painted voxel, voxel index) pairs
+        if pred.shape[1] * pred.shape[2] * pred.shape[3] <= 20000:
+            for tag, use_mws in (('cc', False), ('mws', True)):
+                graph = apg.setAffgraph(g['aff'], g['pairs'])
+                z = np.zeros(pred.shape[1:], np.uint16)
+                stack, _ = g2l.affGraphToInstances(
+                    graph, pred, ps, ps // 2, None, None, z, g['gate'], mws=use_mws,
+                    one_instance_per_channel=True, patch_threshold=kw['patch_threshold'],
+                    debug=False)
+                res['opc_%s/%s' % (tag, name)] = np.packbits(stack > 0)
+                res['opc_%s_shape/%s' % (tag, name)] = np.array(stack.shape, np.int32)
+                vals = np.array([np.unique(c[c > 0]).tolist() or [0] for c in stack], np.int32)
+                res['opc_%s_vals/%s' % (tag, name)] = vals.reshape(-1)
     rng = np.random.default_rng(99)
     n_graphs = 24
     for gi in range(n_graphs):
