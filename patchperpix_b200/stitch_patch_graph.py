@@ -77,6 +77,24 @@ class VolumeInputs:
         self.numinst_prob = numinst_prob
         self.fg = fg
         self.shape = tuple(int(s) for s in pred.shape[-3:])
+        self.device_pred = None
+
+    def to_device(self, max_fraction=0.4):
+        """keep the whole prediction volume resident in HBM when it fits (blocks,
+        face regions and the patch vectors of the final painting are then sliced
+        on the device instead of being gathered with strided host copies).
+        Returns True if the volume is resident."""
+        import torch
+        if self.device_pred is not None:
+            return True
+        if not torch.cuda.is_available():
+            return False
+        free, _ = torch.cuda.mem_get_info()
+        nbytes = int(np.prod(self.pred.shape)) * np.dtype(self.pred.dtype).itemsize
+        if nbytes > max_fraction * free:
+            return False
+        self.device_pred = torch.from_numpy(np.ascontiguousarray(self.pred)).cuda()
+        return True
 
     def _fg_numinst(self, start, stop, **kwargs):
         """foreground / numinst of a region, precedence as in the reference's
@@ -107,8 +125,12 @@ class VolumeInputs:
     def region(self, start, stop, **kwargs):
         """(block, foreground bool, mask, numinst, start_clipped) of
         blockwise_vote_instances (stitch_patch_graph.py:603-637)."""
-        block, s = load_region(self.pred, start, stop)
-        block = np.ascontiguousarray(block)
+        if self.device_pred is not None:
+            block, s = load_region(self.device_pred, start, stop)
+            block = block.contiguous()
+        else:
+            block, s = load_region(self.pred, start, stop)
+            block = np.ascontiguousarray(block)
         foreground, numinst = self._fg_numinst(start, stop, **kwargs)
         mask = np.copy(foreground)
         return block, foreground, mask, numinst, s
@@ -224,6 +246,8 @@ def stitch_arrays(inputs, block_fn=default_block_fn, paint_fn=None, **kwargs):
     kwargs = dict(kwargs, chunksize=chunksize)
     offsets = get_offsets(shape, chunksize)
     nblk = len(offsets)
+    if block_fn is default_block_fn and kwargs.get('ppp_device_volume', True):
+        inputs.to_device()               # whole volume in HBM when it fits
 
     # ---- phase 1: blocks, round-robin over the ranks (offsets.py:45) -----------
     mine = {}
@@ -332,13 +356,15 @@ def paint_global(inputs, pairs, aff, rank=0, world=1, **kwargs):
     P = int(np.prod(ps))
     # gather the patch vectors of my nodes from the host volume (:380-385)
     z, y, x = nodes // (Y * X), (nodes // X) % Y, nodes % X
-    patches = np.ascontiguousarray(
-        np.asarray(inputs.pred)[:, z, y, x].T.astype(np.float32)) if len(nodes) else \
-        np.zeros((0, P), np.float32)
     inst = torch.zeros(shape, dtype=torch.int32, device=dev)
     if len(nodes):
         nd = torch.from_numpy(nodes.astype(np.int32)).to(dev)
-        pt = torch.from_numpy(patches).to(dev)
+        if getattr(inputs, 'device_pred', None) is not None:
+            zi, yi, xi = (torch.from_numpy(a).to(dev) for a in (z, y, x))
+            pt = inputs.device_pred[:, zi, yi, xi].T.float().contiguous()
+        else:
+            patches = np.ascontiguousarray(np.asarray(inputs.pred)[:, z, y, x].T.astype(np.float32))
+            pt = torch.from_numpy(patches).to(dev)
         cc.call('ppp_paint_patches', cc.ptr(pt), cc.ptr(nd), len(nodes), cc.ptr(comp), cfg,
                 cc.ptr(inst), stream)
     dist = _dist()

@@ -2,7 +2,7 @@
 """blockwise assembly of a synthetic 3-D volume under torchrun (NCCL): every
 rank takes blocks / face jobs round-robin; rank 0 prints a digest of the labels
 so that runs with different world sizes can be compared.
-usage: torchrun --nproc-per-node N tools/run_blockwise_dist.py [Z Y X]"""
+usage: [PPP_CHUNK=z,y,x] [PPP_MWS=1] torchrun --nproc-per-node N tools/run_blockwise_dist.py [Z Y X]"""
 import hashlib
 import os
 import sys
@@ -30,8 +30,9 @@ def main():
     labels, numinst = synth.neurites_3d(shape, n=max(4, int(np.prod(shape)) // 60000), seed=4,
                                         radius=(2, 3), seg_len=12.0, n_seg=30)
     pred = synth.patches_from_labels(labels, ps, seed=4).astype(np.float16)
-    kw = dict(bench.KW, patchshape=[7, 7, 7], chunksize=[24, 80, 80], blockwise=True,
-              numinst_key=None, fg_key=None)
+    chunk = [int(v) for v in os.environ.get('PPP_CHUNK', '24,80,80').split(',')]
+    kw = dict(bench.KW, patchshape=[7, 7, 7], chunksize=chunk, blockwise=True,
+              numinst_key=None, fg_key=None, mws=os.environ.get('PPP_MWS', '0') == '1')
     inputs = spg.VolumeInputs(pred)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
