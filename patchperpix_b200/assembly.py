@@ -106,7 +106,8 @@ class BlockAssembler:
     def consensus(self, want_cnt=False, impl=None):
         """create_consensus_array_cuda (consensus_array.py:71-206).
 
-        impl 0 = tiled kernels (default), 1 = simple gather (cross-check)."""
+        impl 0 = automatic (bit-guided gather for psx < 16, tiled TMA kernel
+        otherwise), 1 = simple gather (cross-check), 2 / 3 force one of the two."""
         torch = _torch()
         if not self._prepared:
             self.prepare()

@@ -1,7 +1,11 @@
 // Steps 3+4: greedy foreground cover and greedy set-cover thinning on the
 // device (foreground_cover.py:15-256 are serial python loops over numpy
-// windows).  The decisions are inherently sequential, so both run in ONE CTA;
-// what makes them fast is the data layout: the mask to cover is a bit volume
+// windows).  Both are restated so that the serial walk disappears where the
+// result allows it: the threshold-0 cover is "first coverer of every voxel"
+// (cover_first_*), the set cover runs in rounds of local maxima
+// (thin_rounds_kernel); the one-decision-per-step kernels (cover_kernel for the
+// dense threshold schedule, thin_kernel as cross-check) stay in one CTA.
+// What makes the counting fast is the data layout: the mask to cover is a bit volume
 // (one 32-bit word per 32 x-voxels, resident in shared memory when it fits)
 // and every candidate patch is a P-bit string (`fcmask`, patch > fc_threshold),
 // so "how many uncovered voxels would this patch cover" is a handful of
