@@ -181,6 +181,12 @@ int ppp_mws_host(const uint32_t* pairs, const float* aff, int64_t n,
                  const ppp_cfg* cfg, int32_t* node_vox, int32_t* node_label,
                  int64_t* n_nodes, int32_t* n_labels);
 
+/* HOST helper for the pair enumeration (aff_patch_graph.py:57-110): order[k] =
+ * index of the k-th pair that CPython yields when iterating the set built by
+ * inserting the tuples (pairs[i][0], pairs[i][1]) one by one -- what the reference
+ * does with cKDTree.query_pairs' result.  pairs i64 [n][2], non-negative, distinct. */
+int ppp_pyset_order(const int64_t* pairs, int64_t n, int64_t* order);
+
 /* instances i32 [V] (zeroed by the caller): for every node with comp > 0,
  * window pixels with pred > pt_gt take max(comp) ("later components overwrite
  * earlier ones", graph_to_labeling.py:84).  nodes[m] voxel indices. */

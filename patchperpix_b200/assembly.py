@@ -19,6 +19,43 @@ def _torch():
     return torch
 
 
+_PYSET_REPLAY = None
+
+
+def _pyset_replay_ok():
+    """ppp_pyset_order replays CPython's set table; verified once per process
+    against a real set (another interpreter version may hash or grow differently)."""
+    global _PYSET_REPLAY
+    if _PYSET_REPLAY is None:
+        ok = True
+        rng = np.random.default_rng(12345)
+        for n in (7, 300, 9000):
+            a = np.unique(rng.integers(0, 4 * n, (n, 2)).astype(np.int64), axis=0)
+            rng.shuffle(a)
+            a = np.ascontiguousarray(a)
+            order = np.zeros(len(a), np.int64)
+            cc.call('ppp_pyset_order', a.ctypes.data, len(a), order.ctypes.data)
+            want = np.array(list(set(map(tuple, a.tolist()))), np.int64).reshape(-1, 2)
+            ok = ok and np.array_equal(a[order], want)
+        _PYSET_REPLAY = bool(ok)
+    return _PYSET_REPLAY
+
+
+def query_pairs_set_order(tree, r):
+    """tree.query_pairs(r, p=1) as an int64 [n,2] array in the order in which
+    python iterates over the SET scipy returns (the reference's enumeration order,
+    aff_patch_graph.py:57-110) -- without building the set."""
+    if _pyset_replay_ok():
+        a = np.ascontiguousarray(tree.query_pairs(r, p=1, output_type='ndarray'), np.int64)
+        if len(a) == 0:
+            return a.reshape(0, 2)
+        order = np.zeros(len(a), np.int64)
+        cc.call('ppp_pyset_order', a.ctypes.data, len(a), order.ctypes.data)
+        return a[order]
+    pairs = tree.query_pairs(r, p=1)
+    return np.array(list(pairs), dtype=np.int64).reshape(-1, 2)
+
+
 def mutex_watershed(pairs, aff, cfg):
     """graph_mws.mws on the graph of setAffgraph (graph_mws.py:7-85,
     aff_patch_graph.py:31-40) through ppp_mws_host: the one serial graph pass of
@@ -219,10 +256,9 @@ class BlockAssembler:
         ordr = np.argsort(sel_coords[:, 2], kind='stable')       # :45
         pts = sel_coords[ordr].astype(np.uint32)
         tree = scipy.spatial.cKDTree(pts, leafsize=4)
-        pairs = tree.query_pairs(2 * np.sum(ps), p=1)            # :57
+        pa = query_pairs_set_order(tree, 2 * np.sum(ps))         # :57
         max_ps = kw.get("max_total_patch_distance_in_ps_multiples", 2)
-        if len(pairs):
-            pa = np.array(list(pairs), dtype=np.int64).reshape(-1, 2)
+        if len(pa):
             d = np.abs(pts[pa[:, 0]].astype(np.float32) - pts[pa[:, 1]].astype(np.float32))
             keep = ~np.any(d > max_ps * ps, axis=1)              # :61-69
             pa = pa[keep]

@@ -150,3 +150,98 @@ extern "C" int ppp_mws_host(const uint32_t* pairs, const float* aff, int64_t n,
     *n_labels = (int32_t)members.size() - 1;
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+// Order in which CPython iterates over set((i0,j0), (i1,j1), ...) built by
+// inserting the pairs one by one.  The reference enumerates its patch pairs by
+// iterating the python set that scipy's cKDTree.query_pairs returns
+// (aff_patch_graph.py:57-110, stitch_patch_graph.py:236-258), and that order
+// decides the numbering of the instances.  Building the set of tuples and
+// turning it back into an array dominates the host side of a block (3 of 8 ms on
+// a 98^3 block), so the table is replayed here instead: tuple hash (xxHash-style,
+// Objects/tupleobject.c, CPython >= 3.8), open addressing with 9 linear probes
+// and a perturbed jump, growth x4 at 60 % fill (Objects/setobject.c).  The python
+// side checks this against a real set once per process and falls back to it on
+// any difference (other interpreter version).
+// pairs i64 [n][2] (non-negative, distinct); order i64 [n] out: order[k] = index
+// of the k-th pair the set yields.
+// ---------------------------------------------------------------------------
+namespace {
+
+inline uint64_t py_tuple2_hash(uint64_t a, uint64_t b)
+{
+    const uint64_t P1 = 11400714785074694791ULL, P2 = 14029467366897019727ULL,
+                   P5 = 2870177450012600261ULL;
+    uint64_t acc = P5;
+    const uint64_t lanes[2] = {a, b};
+    for (int i = 0; i < 2; i++) {
+        acc += lanes[i] * P2;
+        acc = (acc << 31) | (acc >> 33);
+        acc *= P1;
+    }
+    acc += 2ULL ^ (P5 ^ 3527539ULL);
+    if (acc == (uint64_t)-1) return 1546275796ULL;
+    return acc;
+}
+
+struct PySetReplay {
+    std::vector<int64_t> slot;        // index of the pair in a table slot, -1 = unused
+    const std::vector<uint64_t>& hash;
+    size_t mask, fill;
+    explicit PySetReplay(const std::vector<uint64_t>& h) : slot(8, -1), hash(h), mask(7), fill(0) {}
+    static void insert_clean(std::vector<int64_t>& t, size_t mask, int64_t key, uint64_t h)
+    {
+        size_t perturb = h, i = (size_t)h & mask;
+        while (true) {
+            if (t[i] < 0) { t[i] = key; return; }
+            if (i + 9 <= mask)
+                for (size_t j = 1; j <= 9; j++)
+                    if (t[i + j] < 0) { t[i + j] = key; return; }
+            perturb >>= 5;
+            i = (i * 5 + 1 + perturb) & mask;
+        }
+    }
+    void add(int64_t key)
+    {
+        const uint64_t h = hash[key];
+        size_t perturb = h, i = (size_t)h & mask;
+        while (true) {
+            const size_t probes = (i + 9 <= mask) ? 9 : 0;
+            bool placed = false;
+            for (size_t j = 0; j <= probes; j++)
+                if (slot[i + j] < 0) { slot[i + j] = key; placed = true; break; }
+            if (placed) break;
+            perturb >>= 5;
+            i = (i * 5 + 1 + perturb) & mask;
+        }
+        fill++;
+        if (fill * 5 < mask * 3) return;
+        const size_t minused = fill > 50000 ? fill * 2 : fill * 4;
+        size_t newsize = 8;
+        while (newsize <= minused) newsize <<= 1;
+        std::vector<int64_t> t(newsize, -1);
+        for (size_t s = 0; s <= mask; s++)
+            if (slot[s] >= 0) insert_clean(t, newsize - 1, slot[s], hash[slot[s]]);
+        slot.swap(t);
+        mask = newsize - 1;
+    }
+};
+
+}  // namespace
+
+extern "C" int ppp_pyset_order(const int64_t* pairs, int64_t n, int64_t* order)
+{
+    if (n < 0 || (n > 0 && (!pairs || !order))) return ppp_fail(-1, "ppp_pyset_order: null argument");
+    std::vector<uint64_t> h((size_t)n);
+    for (int64_t k = 0; k < n; k++) {
+        if (pairs[2 * k] < 0 || pairs[2 * k + 1] < 0)
+            return ppp_fail(-1, "ppp_pyset_order: negative index");
+        h[k] = py_tuple2_hash((uint64_t)pairs[2 * k], (uint64_t)pairs[2 * k + 1]);
+    }
+    PySetReplay set(h);
+    for (int64_t k = 0; k < n; k++) set.add(k);
+    int64_t out = 0;
+    for (size_t s = 0; s <= set.mask; s++)
+        if (set.slot[s] >= 0) order[out++] = set.slot[s];
+    return out == n ? 0 : ppp_fail(-1, "ppp_pyset_order: internal error");
+}

@@ -173,10 +173,10 @@ def face_pairs(cur, nb, ps):
     reference's (python-set) order.  Returns (candidates, pairs index array)."""
     candidates = np.concatenate([cur, nb])
     tree = scipy.spatial.cKDTree(candidates, leafsize=4)
-    pairs = tree.query_pairs(1 * np.sum(ps + 1), p=1)
-    if len(pairs) == 0:
+    from .assembly import query_pairs_set_order
+    pa = query_pairs_set_order(tree, 1 * np.sum(ps + 1))
+    if len(pa) == 0:
         return candidates, np.zeros((0, 2), np.int64)
-    pa = np.array(list(pairs), dtype=np.int64).reshape(-1, 2)
     d = np.abs(candidates[pa[:, 0]].astype(np.float32) -
                candidates[pa[:, 1]].astype(np.float32))
     keep = ~np.any(d > ps + 1, axis=1)                           # remove_pairs :75-88

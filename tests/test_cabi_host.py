@@ -84,3 +84,30 @@ def test_no_cpu_fallback():
         vi.to_instance_seg(np.zeros((9, 1, 8, 8), np.float32), np.zeros((1, 8, 8), bool),
                            np.zeros((1, 8, 8), bool), np.zeros((1, 8, 8), np.uint8),
                            np.array([1, 3, 3]), cuda=False)
+
+
+@pytest.mark.parametrize('n', [0, 1, 5, 6, 40, 1000, 30000, 120000])
+def test_pyset_order_replays_cpython_sets(n):
+    """ppp_pyset_order (host helper of the pair enumeration) against a real set,
+    across every table size up to the x2 growth regime (> 50000 entries)."""
+    from patchperpix_b200 import cuda_code as cc
+    rng = np.random.default_rng(n)
+    a = np.unique(rng.integers(0, max(4, 3 * n), (n, 2)).astype(np.int64), axis=0)
+    rng.shuffle(a)
+    a = np.ascontiguousarray(a)
+    order = np.zeros(len(a), np.int64)
+    cc.call('ppp_pyset_order', a.ctypes.data if len(a) else None, len(a),
+            order.ctypes.data if len(a) else None)
+    want = np.array(list(set(map(tuple, a.tolist()))), np.int64).reshape(-1, 2)
+    assert np.array_equal(a[order], want)
+
+
+def test_query_pairs_set_order_equals_python_set():
+    import scipy.spatial
+    from patchperpix_b200.assembly import query_pairs_set_order
+    rng = np.random.default_rng(3)
+    pts = rng.integers(0, 120, (700, 3)).astype(np.uint32)
+    tree = scipy.spatial.cKDTree(pts, leafsize=4)
+    for r in (4, 21, 42):
+        want = np.array(list(tree.query_pairs(r, p=1)), np.int64).reshape(-1, 2)
+        assert np.array_equal(query_pairs_set_order(tree, r), want)
