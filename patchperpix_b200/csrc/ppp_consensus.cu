@@ -196,61 +196,95 @@ consensus_bits_kernel(const float* __restrict__ dp, const unsigned long long* __
                       float* __restrict__ cons, uint32_t* __restrict__ cnt)
 {
     Geo g = make_geo(cfg);
+    extern __shared__ __align__(16) unsigned char cb_smem[];
+    const int nrw = g.psz * g.psy;
+    unsigned long long* s_rb = (unsigned long long*)cb_smem;     // [nrw][2] bits of this row
+    int32_t* s_prow = (int32_t*)(s_rb + 2 * nrw);                // [K] partner row of a live slot
+    uint16_t* s_k = (uint16_t*)(s_prow + g.K);                   // [K] its slot index
+    __shared__ int s_n;
     const int64_t row = blockIdx.x;
     const int vb = rowvox[row];
     int bz, by, bx;
     vox_decode(g, vb, bz, by, bx);
     const bool gated = (flags[vb] & PPP_FLAG_GATED) != 0;
-    const int nrw = g.psz * g.psy;
     const unsigned long long* rb = rbits + row * nrw * 2;
-    for (int k = threadIdx.x; k < g.K; k += blockDim.x) {
-        float out = 0.0f;
-        uint32_t outc = 0;
+    for (int i = threadIdx.x; i < 2 * nrw; i += blockDim.x) s_rb[i] = rb[i];
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    // pass 1: slots with a gated partner are compacted, the others written as zeros
+    const int lane = threadIdx.x & 31;
+    for (int k0 = 0; k0 < g.K; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        int prow = -1;
+        if (k < g.K && gated) {
+            int lin = k + g.K + 1;
+            int ox = lin % g.nx - (g.psx - 1);
+            int t = lin / g.nx;
+            int oy = t % g.ny - (g.psy - 1);
+            int oz = t / g.ny - (g.psz - 1);
+            int pz = bz + oz, py = by + oy, px = bx + ox;
+            if (pz >= 0 && pz < g.Z && py >= 0 && py < g.Y && px >= 0 && px < g.X) {
+                int vp = (pz * g.Y + py) * g.X + px;
+                if (flags[vp] & PPP_FLAG_GATED) prow = fgidx[vp];
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, prow >= 0);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_n, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (prow >= 0) {
+            int idx = base + __popc(bal & ((1u << lane) - 1u));
+            s_prow[idx] = prow;
+            s_k[idx] = (uint16_t)k;
+        } else if (k < g.K) {
+            cnt[row * g.K + k] = 0;
+            cons[row * g.K + k] = 0.0f;
+        }
+    }
+    __syncthreads();
+    // pass 2: counters from the class bits, sums over the centres that vote
+    const int n = s_n;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int k = s_k[idx];
+        const unsigned long long* rp = rbits + (int64_t)s_prow[idx] * nrw * 2;
         int lin = k + g.K + 1;
         int ox = lin % g.nx - (g.psx - 1);
         int t = lin / g.nx;
         int oy = t % g.ny - (g.psy - 1);
         int oz = t / g.ny - (g.psz - 1);
-        int pz = bz + oz, py = by + oy, px = bx + ox;
-        if (gated && pz >= 0 && pz < g.Z && py >= 0 && py < g.Y && px >= 0 && px < g.X) {
-            int vp = (pz * g.Y + py) * g.X + px;
-            if (flags[vp] & PPP_FLAG_GATED) {
-                const unsigned long long* rp = rbits + (int64_t)fgidx[vp] * nrw * 2;
-                int pos = 0, neg = 0;
-                float sum = 0.0f;
-                int dz0 = max(-g.rz, oz - g.rz), dz1 = min(g.rz, oz + g.rz);
-                int dy0 = max(-g.ry, oy - g.ry), dy1 = min(g.ry, oy + g.ry);
-                for (int dz = dz0; dz <= dz1; dz++)
-                for (int dy = dy0; dy <= dy1; dy++) {
-                    int w1 = (dz + g.rz) * g.psy + (dy + g.ry);
-                    int w2 = (dz - oz + g.rz) * g.psy + (dy - oy + g.ry);
-                    unsigned long long h1 = rb[2 * w1], l1 = rb[2 * w1 + 1];
-                    unsigned long long h2 = rp[2 * w2], l2 = rp[2 * w2 + 1];
-                    if (ox >= 0) { h2 <<= ox; l2 <<= ox; } else { h2 >>= -ox; l2 >>= -ox; }
-                    pos += __popcll(h1 & h2);
-                    neg += __popcll(h1 & l2) + __popcll(l1 & h2);
-                    unsigned long long m = (h1 & (h2 | l2)) | (l1 & h2);   // centres that vote
-                    if (!m || cfg.prod_mode == 0) continue;
-                    const int64_t cline = ((int64_t)(bz + dz) * g.Y + (by + dy)) * g.X;
-                    // patch rows that talk about b and about b + o, seen from this centre line
-                    const int64_t pr1 = (int64_t)((g.rz - dz) * g.psy + (g.ry - dy)) * F;
-                    const int64_t pr2 = (int64_t)((g.rz - dz + oz) * g.psy + (g.ry - dy + oy)) * F;
-                    while (m) {
-                        int tb = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        int cx = bx - g.rx + tb;
-                        int64_t rc = fgidx[cline + cx];
-                        float d1 = dp[(pr1 + rc) * g.rsg + DP_GUARD + (bx - cx + g.rx)];
-                        float d2 = dp[(pr2 + rc) * g.rsg + DP_GUARD + (px - cx + g.rx)];
-                        sum = fmaf(d1, d2, sum);
-                    }
-                }
-                out = consensus_epilogue(cfg, sum, pos, neg);
-                outc = ((uint32_t)neg << 16) | (uint32_t)pos;
+        const int px = bx + ox;
+        int pos = 0, neg = 0;
+        float sum = 0.0f;
+        int dz0 = max(-g.rz, oz - g.rz), dz1 = min(g.rz, oz + g.rz);
+        int dy0 = max(-g.ry, oy - g.ry), dy1 = min(g.ry, oy + g.ry);
+        for (int dz = dz0; dz <= dz1; dz++)
+        for (int dy = dy0; dy <= dy1; dy++) {
+            int w1 = (dz + g.rz) * g.psy + (dy + g.ry);
+            int w2 = (dz - oz + g.rz) * g.psy + (dy - oy + g.ry);
+            unsigned long long h1 = s_rb[2 * w1], l1 = s_rb[2 * w1 + 1];
+            const ulonglong2 hl = *(const ulonglong2*)(rp + 2 * w2);
+            unsigned long long h2 = hl.x, l2 = hl.y;
+            if (ox >= 0) { h2 <<= ox; l2 <<= ox; } else { h2 >>= -ox; l2 >>= -ox; }
+            pos += __popcll(h1 & h2);
+            neg += __popcll(h1 & l2) + __popcll(l1 & h2);
+            unsigned long long m = (h1 & (h2 | l2)) | (l1 & h2);   // centres that vote
+            if (!m || cfg.prod_mode == 0) continue;
+            const int64_t cline = ((int64_t)(bz + dz) * g.Y + (by + dy)) * g.X;
+            // patch rows that talk about b and about b + o, seen from this centre line
+            const int64_t pr1 = (int64_t)((g.rz - dz) * g.psy + (g.ry - dy)) * F;
+            const int64_t pr2 = (int64_t)((g.rz - dz + oz) * g.psy + (g.ry - dy + oy)) * F;
+            while (m) {
+                int tb = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                int cx = bx - g.rx + tb;
+                int64_t rc = fgidx[cline + cx];
+                float d1 = dp[(pr1 + rc) * g.rsg + DP_GUARD + (bx - cx + g.rx)];
+                float d2 = dp[(pr2 + rc) * g.rsg + DP_GUARD + (px - cx + g.rx)];
+                sum = fmaf(d1, d2, sum);
             }
         }
-        cons[row * g.K + k] = out;
-        cnt[row * g.K + k] = outc;
+        cons[row * g.K + k] = consensus_epilogue(cfg, sum, pos, neg);
+        cnt[row * g.K + k] = ((uint32_t)neg << 16) | (uint32_t)pos;
     }
 }
 
@@ -726,7 +760,13 @@ extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8
     }
     if (impl == 2 || (impl == 0 && g.psx < 16)) {
         if (g.psx > 64) return ppp_fail(-1, "ppp_consensus: psx > 64 needs the tiled kernel");
-        consensus_bits_kernel<<<(unsigned)F, 128, 0, s>>>(
+        if (g.K > 65535) return ppp_fail(-1, "ppp_consensus: more than 65535 offsets");
+        size_t bsm = (size_t)g.psz * g.psy * 16 + (size_t)g.K * 6 + 16;
+        cudaError_t be = cudaFuncSetAttribute(consensus_bits_kernel,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)bsm);
+        if (be != cudaSuccess) return ppp_fail((int)be, "ppp_consensus: smem attribute (bits)");
+        consensus_bits_kernel<<<(unsigned)F, 128, bsm, s>>>(
             dp, (const unsigned long long*)rbits, flags, fgidx, rowvox, F, *cfg, cons, cnt);
         return ppp_check("ppp_consensus(bits)");
     }
