@@ -152,11 +152,14 @@ int ppp_thin(const uint8_t* mask, const int32_t* sel, int64_t m,
 /* ---- step 5: patch graph (computePatchGraph.cu) ---------------------------
  * pairs u32 [n][6] = (z,y,x,z2,y2,x2); aff f32 [n].  Default: the terms are
  * added into one float in the reference's loop order (the mutex watershed
- * orders edges by |aff|); graph_flags bit2: parallel sum in double. */
+ * orders edges by |aff|); graph_flags bit2: parallel sum in double.
+ * scratch: ppp_patch_graph_scratch_bytes(cfg, n) (the voting-pixel lists of the
+ * pairs; may be NULL with graph_flags bit2). */
+int64_t ppp_patch_graph_scratch_bytes(const ppp_cfg* cfg, int64_t n);
 int ppp_patch_graph(const float* pred, const uint8_t* flags,
                     const int32_t* fgidx, const float* cons,
                     const uint32_t* pairs, int64_t n, const ppp_cfg* cfg,
-                    float* aff, void* stream);
+                    float* aff, void* scratch, void* stream);
 
 /* ---- step 6: connected components over aff > 0 and painting ---------------
  * (aff_patch_graph.py:31-40, graph_to_labeling.py:50-84).  Node = voxel index

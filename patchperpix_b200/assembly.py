@@ -287,8 +287,11 @@ class BlockAssembler:
         cfg = self.cfg
         if fast is not None:
             cfg = cc.make_cfg(self.shape, self.ps, **dict(self.kwargs, ppp_graph_fast=fast))
+        scratch = torch.empty(cc.call('ppp_patch_graph_scratch_bytes', cfg, n),
+                              dtype=torch.uint8, device=self.dev)
         cc.call('ppp_patch_graph', cc.ptr(self.pred), cc.ptr(self.flags), cc.ptr(self.fgidx),
-                cc.ptr(self.cons), cc.ptr(pairs_dev), n, cfg, cc.ptr(aff), self.stream)
+                cc.ptr(self.cons), cc.ptr(pairs_dev), n, cfg, cc.ptr(aff), cc.ptr(scratch),
+                self.stream)
         return aff[:n]
 
     # -- step 6 ------------------------------------------------------------

@@ -239,11 +239,15 @@ template <bool LCG>
 __global__ void __launch_bounds__(PGR_THREADS)
 patch_graph_ref_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags,
                        const int32_t* __restrict__ fgidx, const float* __restrict__ cons,
-                       const uint32_t* __restrict__ pairs, ppp_cfg cfg, float* __restrict__ aff)
+                       const uint32_t* __restrict__ pairs, ppp_cfg cfg, float* __restrict__ aff,
+                       int32_t* __restrict__ lists)
 {
     Geo g = make_geo(cfg);
-    extern __shared__ unsigned char smem_raw[];
-    int32_t* s_q1 = (int32_t*)smem_raw;           // [P] per list: packed coordinates,
+    // the two pixel lists of this pair live in GLOBAL scratch (written once, then read
+    // through L1/L2 by the producer warps: the same i for consecutive terms, consecutive
+    // j): the CTA needs almost no shared memory, so enough pairs are resident per SM to
+    // run every serial chain of the launch side by side
+    int32_t* s_q1 = lists + (int64_t)blockIdx.x * (LCG ? 6 : 4) * g.P;   // [P] packed coordinates,
     int32_t* s_row1 = s_q1 + g.P;                 //     consensus row,
     int32_t* s_q2 = s_row1 + g.P;
     int32_t* s_row2 = s_q2 + g.P;
@@ -377,10 +381,16 @@ patch_graph_ref_kernel(const float* __restrict__ pred, const uint8_t* __restrict
     }
 }
 
+extern "C" int64_t ppp_patch_graph_scratch_bytes(const ppp_cfg* cfg, int64_t n)
+{
+    Geo g = make_geo(*cfg);
+    return (n > 0 ? n : 0) * (int64_t)g.P * 24 + 256;     // two pixel lists per pair
+}
+
 extern "C" int ppp_patch_graph(const float* pred, const uint8_t* flags,
                                const int32_t* fgidx, const float* cons,
                                const uint32_t* pairs, int64_t n, const ppp_cfg* cfg,
-                               float* aff, void* stream)
+                               float* aff, void* scratch, void* stream)
 {
     if (n <= 0) return 0;
     Geo g = make_geo(*cfg);
@@ -391,19 +401,13 @@ extern "C" int ppp_patch_graph(const float* pred, const uint8_t* flags,
         // rnd0 = z*z2*y*y2*x*x2 (computePatchGraph.cu:24-27) is 0 for every pair of a
         // single-slice volume: no sub-sampling, no factor tables
         const bool lcg = g.Z > 1;
-        size_t smem = (size_t)g.P * (lcg ? 24 : 16) + 16;
-        cudaError_t e = lcg
-            ? cudaFuncSetAttribute(patch_graph_ref_kernel<true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-            : cudaFuncSetAttribute(patch_graph_ref_kernel<false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return ppp_fail((int)e, "ppp_patch_graph: smem attribute");
+        if (scratch == nullptr) return ppp_fail(-1, "ppp_patch_graph: scratch required");
         if (lcg)
-            patch_graph_ref_kernel<true><<<(unsigned)n, PGR_THREADS, smem, (cudaStream_t)stream>>>(
-                pred, flags, fgidx, cons, pairs, *cfg, aff);
+            patch_graph_ref_kernel<true><<<(unsigned)n, PGR_THREADS, 0, (cudaStream_t)stream>>>(
+                pred, flags, fgidx, cons, pairs, *cfg, aff, (int32_t*)scratch);
         else
-            patch_graph_ref_kernel<false><<<(unsigned)n, PGR_THREADS, smem, (cudaStream_t)stream>>>(
-                pred, flags, fgidx, cons, pairs, *cfg, aff);
+            patch_graph_ref_kernel<false><<<(unsigned)n, PGR_THREADS, 0, (cudaStream_t)stream>>>(
+                pred, flags, fgidx, cons, pairs, *cfg, aff, (int32_t*)scratch);
         return ppp_check("ppp_patch_graph(reference order)");
     }
     size_t smem = (size_t)g.P * 12 + 16;

@@ -118,7 +118,8 @@ _SIGS = {
     'ppp_cover': (ctypes.c_int, ['p', 'p', 'p', 'i64', 'p', 'p', 'cfg', 'p', 'i32', 'p', 'p', 'p']),
     'ppp_thin_scratch_bytes': (ctypes.c_int64, ['cfg', 'i64']),
     'ppp_thin': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'p', 'cfg', 'p', 'p', 'p']),
-    'ppp_patch_graph': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p']),
+    'ppp_patch_graph_scratch_bytes': (ctypes.c_int64, ['cfg', 'i64']),
+    'ppp_patch_graph': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
     'ppp_label_scratch_bytes': (ctypes.c_int64, ['i64', 'i64']),
     'ppp_label_cc': (ctypes.c_int, ['p', 'p', 'i64', 'cfg', 'p', 'p', 'p', 'p']),
     'ppp_mws_host': (ctypes.c_int, ['p', 'p', 'i64', 'cfg', 'p', 'p', 'p', 'p']),
