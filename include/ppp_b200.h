@@ -92,7 +92,7 @@ int ppp_compact(const uint8_t* flags, int64_t V, int32_t* fgidx, int32_t* rowvox
 /* ---- step 0b: centre-major class-folded patches + bit masks --------------
  * dp f32 [F][P]; fcmask/ptmask u32 [F][W], W = (P+31)/32: bit po set iff
  * pred[po][c] > fc_gt / > pt_gt (foreground_cover.py:158, graph_to_labeling.py:84).
- * rbits u64 [F][psz*psy][2]: "received" class bits of every gated voxel — bit
+ * rbits u64 [psz*psy][F][2] (centre-line major): "received" class bits of every gated voxel — bit
  * (dx + rx) of word (dz,dy) says the centre at b + d calls b high (word 0) /
  * background (word 1); the vote counters are popcounts over them.
  * Any output pointer may be NULL. */

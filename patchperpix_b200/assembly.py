@@ -131,7 +131,7 @@ class BlockAssembler:
         self.fcmask = torch.empty((F, self.W), dtype=torch.int32, device=self.dev)
         self.rbits = None
         if want_dp and int(self.ps[2]) <= 64:
-            self.rbits = torch.empty((F, int(self.ps[0] * self.ps[1]), 2), dtype=torch.int64,
+            self.rbits = torch.empty((int(self.ps[0] * self.ps[1]), F, 2), dtype=torch.int64,
                                      device=self.dev)
         cc.call('ppp_prepare_patches', cc.ptr(self.pred), cc.ptr(self.flags),
                 cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.dp),

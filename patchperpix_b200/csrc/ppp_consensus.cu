@@ -97,7 +97,7 @@ consensus_naive_kernel(const float* __restrict__ dp, const uint8_t* __restrict__
 __global__ void __launch_bounds__(256)
 consensus_count_kernel(const unsigned long long* __restrict__ rbits,
                        const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
-                       const int32_t* __restrict__ rowvox, ppp_cfg cfg,
+                       const int32_t* __restrict__ rowvox, int64_t F, ppp_cfg cfg,
                        float* __restrict__ cons, uint32_t* __restrict__ cnt)
 {
     Geo g = make_geo(cfg);
@@ -112,8 +112,8 @@ consensus_count_kernel(const unsigned long long* __restrict__ rbits,
     int bz, by, bx;
     vox_decode(g, vb, bz, by, bx);
     const bool gated = (flags[vb] & PPP_FLAG_GATED) != 0;
-    const unsigned long long* rb = rbits + row * nrw * 2;
-    for (int i = threadIdx.x; i < 2 * nrw; i += blockDim.x) s_rb[i] = rb[i];
+    for (int i = threadIdx.x; i < 2 * nrw; i += blockDim.x)      // rbits is [line][row][2]
+        s_rb[i] = rbits[((int64_t)(i >> 1) * F + row) * 2 + (i & 1)];
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     // pass 1: slots whose partner is gated are compacted (dense warps in pass 2), all
@@ -152,7 +152,7 @@ consensus_count_kernel(const unsigned long long* __restrict__ rbits,
     const int n = s_n;
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
         const int k = s_k[idx];
-        const unsigned long long* rp = rbits + (int64_t)s_prow[idx] * nrw * 2;
+        const unsigned long long* rp = rbits + (int64_t)s_prow[idx] * 2;   // + line * 2F
         int lin = k + g.K + 1;
         int ox = lin % g.nx - (g.psx - 1);
         int t = lin / g.nx;
@@ -167,7 +167,7 @@ consensus_count_kernel(const unsigned long long* __restrict__ rbits,
             int w1 = (dz + g.rz) * g.psy + (dy + g.ry);
             int w2 = (dz - oz + g.rz) * g.psy + (dy - oy + g.ry);
             unsigned long long h1 = s_rb[2 * w1], l1 = s_rb[2 * w1 + 1];
-            const ulonglong2 hl = *(const ulonglong2*)(rp + 2 * w2);
+            const ulonglong2 hl = *(const ulonglong2*)(rp + (int64_t)w2 * 2 * F);
             unsigned long long h2 = hl.x, l2 = hl.y;
             if (ox >= 0) { h2 <<= ox; l2 <<= ox; } else { h2 >>= -ox; l2 >>= -ox; }
             pos += __popcll(h1 & h2);
@@ -207,8 +207,8 @@ consensus_bits_kernel(const float* __restrict__ dp, const unsigned long long* __
     int bz, by, bx;
     vox_decode(g, vb, bz, by, bx);
     const bool gated = (flags[vb] & PPP_FLAG_GATED) != 0;
-    const unsigned long long* rb = rbits + row * nrw * 2;
-    for (int i = threadIdx.x; i < 2 * nrw; i += blockDim.x) s_rb[i] = rb[i];
+    for (int i = threadIdx.x; i < 2 * nrw; i += blockDim.x)      // rbits is [line][row][2]
+        s_rb[i] = rbits[((int64_t)(i >> 1) * F + row) * 2 + (i & 1)];
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     // pass 1: slots with a gated partner are compacted, the others written as zeros
@@ -246,7 +246,7 @@ consensus_bits_kernel(const float* __restrict__ dp, const unsigned long long* __
     const int n = s_n;
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
         const int k = s_k[idx];
-        const unsigned long long* rp = rbits + (int64_t)s_prow[idx] * nrw * 2;
+        const unsigned long long* rp = rbits + (int64_t)s_prow[idx] * 2;   // + line * 2F
         int lin = k + g.K + 1;
         int ox = lin % g.nx - (g.psx - 1);
         int t = lin / g.nx;
@@ -262,7 +262,7 @@ consensus_bits_kernel(const float* __restrict__ dp, const unsigned long long* __
             int w1 = (dz + g.rz) * g.psy + (dy + g.ry);
             int w2 = (dz - oz + g.rz) * g.psy + (dy - oy + g.ry);
             unsigned long long h1 = s_rb[2 * w1], l1 = s_rb[2 * w1 + 1];
-            const ulonglong2 hl = *(const ulonglong2*)(rp + 2 * w2);
+            const ulonglong2 hl = *(const ulonglong2*)(rp + (int64_t)w2 * 2 * F);
             unsigned long long h2 = hl.x, l2 = hl.y;
             if (ox >= 0) { h2 <<= ox; l2 <<= ox; } else { h2 >>= -ox; l2 >>= -ox; }
             pos += __popcll(h1 & h2);
@@ -778,7 +778,7 @@ extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8
                                               (int)csm);
         if (ce != cudaSuccess) return ppp_fail((int)ce, "ppp_consensus: smem attribute (count)");
         consensus_count_kernel<<<(unsigned)F, 256, csm, s>>>(
-            (const unsigned long long*)rbits, flags, fgidx, rowvox, *cfg, cons, cnt);
+            (const unsigned long long*)rbits, flags, fgidx, rowvox, F, *cfg, cons, cnt);
     }
     if (cfg->prod_mode == 0) return ppp_check("ppp_consensus(count)");   // no float sums needed
     const int stages = rows_stages(g);

@@ -240,7 +240,8 @@ prepare_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags
 // calls b "high" (H word) or "background" (L word).  The vote COUNTERS of the
 // consensus are popcounts over these words (ppp_consensus.cu).  Lanes walk
 // consecutive rows, so the dense plane reads are coalesced.
-// rbits u64 [F][psz*psy][2].
+// rbits u64 [psz*psy][F][2] (line major: the consensus kernels read one word pair
+// per centre line from CONSECUTIVE partner rows, which are then contiguous).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 received_bits_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags,
@@ -272,7 +273,7 @@ received_bits_kernel(const float* __restrict__ pred, const uint8_t* __restrict__
             }
         }
     }
-    const int64_t o = (row * (g.psz * g.psy) + w) * 2;
+    const int64_t o = ((int64_t)w * F + row) * 2;
     rbits[o] = hb;
     rbits[o + 1] = lb;
 }

@@ -132,6 +132,9 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
         sc = np.asarray(kwargs['selected_patches'], dtype=np.int64).reshape(-1, 3)
         sel_coords = sc
     else:
+        if order is None:
+            raise NotImplementedError("skipRanking needs selected_patches (a stored ranking "
+                                      "file is outside the B200 hot path)")
         if kwargs.get('skipSelection', False):
             sel = order
         else:
