@@ -317,3 +317,35 @@ def test_streamed_samples_equal_single_calls():
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
     assert list(vi.to_instance_seg_stream(iter([]), ps, **FLY)) == []
+
+
+def test_file_level_entry_point(tmp_path):
+    """vote_instances.main (vote_instances.py:557-605) on `.npy` predictions, single file
+    and directory form: same labels as the array call, foreground-cropped
+    (:535-540), written as `<sample>.npz` (h5py is optional in this image)."""
+    from patchperpix_b200 import vote_instances as vi
+    ps = np.array([1, 9, 9])
+    want = {}
+    d = tmp_path / 'pred'
+    d.mkdir()
+    for seed in (301, 302):
+        pred, _, _ = synth.make_case(kind='worms', patchshape=ps, seed=seed, shape=(40, 56),
+                                     n_worms=3, width=(4, 6), length=(20, 40))
+        fg = pred[40] > np.float32(0.5)
+        np.save(d / ('s%d.npy' % seed), pred[:, 0])              # legacy 2-D layout [P,Y,X]
+        inst, fgo = vi.to_instance_seg(pred.copy(), fg.copy(), fg.copy(), fg.astype(np.uint8),
+                                       ps.copy(), **FLY)
+        inst[fgo == 0] = 0
+        want[seed] = inst
+    kw = {k: v for k, v in FLY.items() if k not in ('return_intermediates', 'pad_with_ps')}
+    out1 = tmp_path / 'one'
+    vi.main(affinities=str(d / 's301.npy'), patchshape=[1, 9, 9], result_folder=str(out1),
+            output_format='npz', check_required=False, **kw)
+    got = np.load(out1 / 's301.npz')
+    assert np.array_equal(got['vote_instances'], want[301])
+    assert got['vote_foreground'].dtype == np.uint8
+    out2 = tmp_path / 'all'
+    vi.main(affinities=str(d), patchshape=[1, 9, 9], result_folder=str(out2),
+            output_format='npz', check_required=False, **kw)
+    for seed in (301, 302):
+        assert np.array_equal(np.load(out2 / ('s%d.npz' % seed))['vote_instances'], want[seed])
