@@ -368,42 +368,39 @@ __device__ __forceinline__ void bulk_load(void* smem, const void* gmem, unsigned
         :: "r"(sa), "l"(gmem), "r"(bytes), "r"(ba) : "memory");
 }
 
-// greedy cover of the gated voxels of one line by T-wide windows; s_out gets the
-// window start x.
-__device__ int ct_tiles_of_line(const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
-                                const int32_t* __restrict__ rowvox, int64_t line_base, int X,
-                                int64_t V, int F, int16_t* s_tmp, int16_t* s_out, int* s_scr)
+// ---------------------------------------------------------------------------
+// pre-pass: greedy cover of the gated voxels of every line by T-wide x-windows
+// ("tiles"), once per line instead of once per (line, offset-row group) CTA.
+// One warp per line; tiles i16 [lines][ts] (ts = ceil(X/T) + 1), ntiles i32 [lines].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+consensus_tiles_kernel(const uint8_t* __restrict__ flags, ppp_cfg cfg, int ts,
+                       int16_t* __restrict__ tiles, int32_t* __restrict__ ntiles)
 {
-    const int ra = rows_before(fgidx, line_base, V, F);
-    const int rb = rows_before(fgidx, line_base + X, V, F);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = CT_THREADS / 32;
-    const bool worker = threadIdx.x < CT_THREADS;      // the producer warp only keeps the barriers
-    int ntot = 0;
-    for (int base = ra; base < rb; base += CT_THREADS) {
-        int r = base + threadIdx.x;
-        int v = (worker && r < rb) ? rowvox[r] : 0;
-        bool ok = worker && r < rb && (flags[v] & PPP_FLAG_GATED);
-        unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) s_scr[w] = __popc(bal);
-        __syncthreads();
-        int off = ntot;
-        for (int q = 0; q < w; q++) off += s_scr[q];
-        if (ok) s_tmp[off + __popc(bal & ((1u << lane) - 1u))] = (int16_t)(v - line_base);
-        for (int q = 0; q < nw; q++) ntot += s_scr[q];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        int n = 0, covered = -1;
-        for (int i = 0; i < ntot; i++) {
-            int x = s_tmp[i];
-            if (x > covered && n < CT_MAXTILES) { s_out[n++] = (int16_t)x; covered = x + CT_T - 1; }
+    Geo g = make_geo(cfg);
+    const int lane = threadIdx.x & 31;
+    const int64_t line = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (line >= (int64_t)g.Z * g.Y) return;
+    const uint8_t* fl = flags + line * g.X;
+    int16_t* out = tiles + line * ts;
+    int n = 0, covered = -1;                       // last x covered by a tile so far
+    for (int x0 = 0; x0 < g.X; x0 += 32) {
+        const int x = x0 + lane;
+        unsigned m = __ballot_sync(0xffffffffu, x < g.X && (fl[x] & PPP_FLAG_GATED));
+        while (m) {                                // uniform over the warp
+            const int b = __ffs(m) - 1;
+            const int xs = x0 + b;
+            if (xs > covered) {
+                if (lane == 0) out[n] = (int16_t)xs;
+                n++;
+                covered = xs + CT_T - 1;
+            }
+            // drop the bits this tile covers
+            const int upto = covered - x0;         // last covered bit of this word
+            m &= upto >= 31 ? 0u : ~((2u << upto) - 1u);
         }
-        s_scr[0] = n;
     }
-    __syncthreads();
-    int n = s_scr[0];
-    __syncthreads();
-    return n;
+    if (lane == 0) ntiles[line] = n;
 }
 
 #ifdef CT_PROFILE
@@ -426,7 +423,8 @@ __global__ void __launch_bounds__(CT_THREADS + 32, CT_MINB)
 consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ flags,
                       const int32_t* __restrict__ fgidx, const int32_t* __restrict__ rowvox,
                       int F, ppp_cfg cfg, const uint32_t* __restrict__ cnt,
-                      float* __restrict__ cons, int S)
+                      float* __restrict__ cons, int S, const int16_t* __restrict__ tiles,
+                      const int32_t* __restrict__ ntiles, int ts)
 {
     constexpr int T = CT_T;
     Geo g = make_geo(cfg);
@@ -441,8 +439,7 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
     int16_t* s_bt = (int16_t*)(s_items + CT_MAXITEMS);           // [MAXTILES] base tile starts
     int16_t* s_pt = s_bt + CT_MAXTILES;                          // [NOY][MAXTILES]
     int16_t* s_tmp = s_pt + NOY * CT_MAXTILES;                   // [XMAX]
-    __shared__ int s_scr[CT_THREADS / 32 + 1];
-    __shared__ int s_npt[NOY], s_nitems;
+    __shared__ int s_nitems;
     __shared__ __align__(8) uint64_t s_full[CT_MAXSTAGES], s_empty[CT_MAXSTAGES];
     __shared__ int2 s_info[CT_MAXSTAGES];                        // (centre line, centres) of a stage
 
@@ -456,13 +453,15 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
     long long t_prof = clock64();
 #endif
 
-    // ---- tiles of the base line ----------------------------------------------
-    const int nbt = ct_tiles_of_line(flags, fgidx, rowvox, bline, g.X, g.V, F, s_tmp, s_bt, s_scr);
+    // ---- tiles of the base line (from the pre-pass) ---------------------------
+    const int nbt = min(ntiles[line], CT_MAXTILES);
     if (nbt == 0) return;
+    for (int i = tid; i < nbt; i += CT_THREADS + 32) s_bt[i] = tiles[(int64_t)line * ts + i];
     // ---- offset rows of this group, their partner lines and tiles --------------
     int oz_t[NOY], oy_t[NOY];
     int64_t pline_t[NOY];
     bool row_ok[NOY];
+    int np_t[NOY];
 #pragma unroll
     for (int t = 0; t < NOY; t++) {
         int orow = blockIdx.x * NOY + t;
@@ -471,41 +470,65 @@ consensus_rows_kernel(const float* __restrict__ dp, const uint8_t* __restrict__ 
         oy_t[t] = rlin % g.ny - (g.psy - 1);
         int pz = bz + oz_t[t], py = by + oy_t[t];
         row_ok[t] = orow < nrows_off && pz >= 0 && pz < g.Z && py >= 0 && py < g.Y;
-        pline_t[t] = row_ok[t] ? ((int64_t)pz * g.Y + py) * g.X : 0;
-        int np = 0;
-        if (row_ok[t])
-            np = ct_tiles_of_line(flags, fgidx, rowvox, pline_t[t], g.X, g.V, F, s_tmp,
-                                  s_pt + t * CT_MAXTILES, s_scr);
-        if (tid == 0) s_npt[t] = np;
+        const int64_t pl = row_ok[t] ? (int64_t)pz * g.Y + py : 0;
+        pline_t[t] = pl * g.X;
+        np_t[t] = row_ok[t] ? min(ntiles[pl], CT_MAXTILES) : 0;
+        for (int i = tid; i < np_t[t]; i += CT_THREADS + 32)
+            s_pt[t * CT_MAXTILES + i] = tiles[pl * ts + i];
     }
     __syncthreads();
-    // ---- work items, base-tile major so that a warp works on one x-neighbourhood --
+    // ---- work items, base-tile major so that a warp works on one x-neighbourhood:
+    // every (base tile, offset row) counts its partner tiles within reach in parallel,
+    // thread 0 turns the counts into offsets, then the items are written in parallel --
+    int32_t* s_cntoff = (int32_t*)s_tmp;                         // [nbt * NOY + 1] (XMAX i16 = 1024 i32)
+    const int nent = nbt * NOY;
+    auto reach = [&](int e, int& lo, int& hi) {                  // partner tiles of entry e
+        const int bt = e / NOY, t = e - bt * NOY;
+        const int b0 = s_bt[bt], np = np_t[t];
+        const int16_t* pt = s_pt + t * CT_MAXTILES;
+        // partner windows [p0, p0+T) with some |p - b| < psx for b in [b0, b0+T)
+        int a = 0, z = np;
+        while (a < z) { int mid = (a + z) >> 1; if (pt[mid] + T - 1 < b0 - (g.psx - 1)) a = mid + 1; else z = mid; }
+        lo = a;
+        a = lo; z = np;
+        while (a < z) { int mid = (a + z) >> 1; if (pt[mid] <= b0 + T - 1 + (g.psx - 1)) a = mid + 1; else z = mid; }
+        hi = a;
+        if ((blockIdx.x * NOY + t) == 0) {                       // offset row (0,0): only p > b is stored
+            a = lo; z = hi;
+            while (a < z) { int mid = (a + z) >> 1; if (pt[mid] + T - 1 <= b0) a = mid + 1; else z = mid; }
+            lo = a;
+        }
+    };
+    for (int e = tid; e < nent; e += CT_THREADS + 32) {
+        int lo, hi;
+        reach(e, lo, hi);
+        s_cntoff[e] = max(hi - lo, 0);
+    }
+    __syncthreads();
     if (tid == 0) {
         int n = 0;
-        int lo[NOY], hi[NOY];
-        for (int t = 0; t < NOY; t++) lo[t] = hi[t] = 0;
-        for (int bt = 0; bt < nbt; bt++) {
-            const int b0 = s_bt[bt];
-            for (int t = 0; t < NOY; t++) {
-                const int np = s_npt[t];
-                const int16_t* pt = s_pt + t * CT_MAXTILES;
-                const bool same = (blockIdx.x * NOY + t) == 0;    // offset row (0,0)
-                // partner windows [p0, p0+T) with some |p - b| < psx for b in [b0, b0+T)
-                while (lo[t] < np && pt[lo[t]] + T - 1 < b0 - (g.psx - 1)) lo[t]++;
-                if (hi[t] < lo[t]) hi[t] = lo[t];
-                while (hi[t] < np && pt[hi[t]] <= b0 + T - 1 + (g.psx - 1)) hi[t]++;
-                for (int q = lo[t]; q < hi[t] && n < CT_MAXITEMS; q++) {
-                    if (same && pt[q] + T - 1 <= b0) continue;    // only p > b is stored
-                    s_items[n++] = ((uint32_t)t << 24) | ((uint32_t)bt << 12) | (uint32_t)q;
-                }
-            }
+        for (int e = 0; e < nent; e++) {
+            int c = s_cntoff[e];
+            if (n + c > CT_MAXITEMS) c = CT_MAXITEMS - n;        // cannot happen: bound checked on the host
+            s_cntoff[e] = n;
+            n += c;
         }
+        s_cntoff[nent] = n;
         s_nitems = n;
         for (int i = 0; i < S; i++) {
             mbar_init(&s_full[i], 1);                             // the producer's expect_tx arrive
             mbar_init(&s_empty[i], CT_THREADS / 32);              // one arrive per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    for (int e = tid; e < nent; e += CT_THREADS + 32) {
+        int lo, hi;
+        reach(e, lo, hi);
+        const int bt = e / NOY, t = e - bt * NOY;
+        const int off = s_cntoff[e], c = s_cntoff[e + 1] - off;
+        for (int q = 0; q < c; q++)
+            s_items[off + q] = ((uint32_t)t << 24) | ((uint32_t)bt << 12) | (uint32_t)(lo + q);
     }
     // ---- row ranges of the centre lines around the base line -------------------
     const int cza = max(bz - g.rz, g.rz), czb = min(bz + g.rz, g.Z - 1 - g.rz);
@@ -721,10 +744,14 @@ static int rows_stages(const Geo& g)
     return s;
 }
 
+static int tiles_stride(const Geo& g) { return (g.X + CT_T - 1) / CT_T + 1; }
+
 extern "C" int64_t ppp_consensus_scratch_bytes(const ppp_cfg* cfg)
 {
-    (void)cfg;
-    return 256;
+    // tile lists of the pre-pass: i16 [lines][ts] + i32 [lines]
+    Geo g = make_geo(*cfg);
+    const int64_t lines = (int64_t)g.Z * g.Y;
+    return ((lines * tiles_stride(g) * 2 + 255) / 256) * 256 + lines * 4 + 256;
 }
 
 extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8_t* flags,
@@ -789,7 +816,13 @@ extern "C" int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8
     int nrows_off = (g.nz * g.ny - 1) / 2 + 1;
     // offset-row groups on x (scheduled first): the groups of one line share its A1 rows in L2
     dim3 grid((unsigned)((nrows_off + CT_NOY - 1) / CT_NOY), (unsigned)(g.Z * g.Y));
+    if (scratch == nullptr) return ppp_fail(-1, "ppp_consensus: scratch required");
+    const int64_t lines = (int64_t)g.Z * g.Y;
+    const int ts = tiles_stride(g);
+    int16_t* tiles = (int16_t*)scratch;
+    int32_t* ntiles = (int32_t*)((char*)scratch + ((lines * ts * 2 + 255) / 256) * 256);
+    consensus_tiles_kernel<<<(unsigned)((lines + 3) / 4), 128, 0, s>>>(flags, *cfg, ts, tiles, ntiles);
     consensus_rows_kernel<CT_NOY><<<grid, CT_THREADS + 32, smem, s>>>(
-        dp, flags, fgidx, rowvox, (int)F, *cfg, cnt, cons, stages);
+        dp, flags, fgidx, rowvox, (int)F, *cfg, cnt, cons, stages, tiles, ntiles, ts);
     return ppp_check("ppp_consensus(rows)");
 }
