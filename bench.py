@@ -48,8 +48,8 @@ KW = dict(patch_threshold=0.5, fc_threshold=0.5, cuda=True, blockwise=False,
           overlapping_inst=True, skipThinCover=False)
 # kernels launched per C-ABI call (counted to report gpu_launches)
 # (own kernels + the CUB radix-sort passes the library launches; checked against
-# the ncu launch list profiles/r1_v8_launches.csv: 45 per step)
-LAUNCHES = dict(ppp_gate=1, ppp_compact=3, ppp_prepare_patches=2, ppp_consensus=2,
+# the ncu launch list profiles/r1_v9_launches.csv: 46 per step)
+LAUNCHES = dict(ppp_gate=1, ppp_compact=3, ppp_prepare_patches=2, ppp_consensus=3,
                 ppp_rank=10, ppp_rank_sort=12, ppp_cover=4, ppp_thin=1, ppp_patch_graph=1,
                 ppp_label_cc=8, ppp_paint=1)
 
@@ -362,7 +362,7 @@ def main():
     b_rank = P * 4 + K * 4 + 4
     # DRAM bytes per launch of the same kernels from the committed ncu capture
     traffic = {}
-    tp = os.path.join(ROOT, 'profiles', 'r1_v8_traffic.json')
+    tp = os.path.join(ROOT, 'profiles', 'r1_v9_traffic.json')
     if os.path.exists(tp):
         traffic = json.load(open(tp))
     line = dict(
