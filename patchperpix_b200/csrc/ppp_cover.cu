@@ -10,6 +10,7 @@
 // and every candidate patch is a P-bit string (`fcmask`, patch > fc_threshold),
 // so "how many uncovered voxels would this patch cover" is a handful of
 // funnel-shift / AND / POPC per patch row instead of a P-element numpy op.
+#include <cub/cub.cuh>
 #include "ppp_common.cuh"
 #include "ppp_api.cuh"
 
@@ -567,6 +568,59 @@ __device__ __forceinline__ int patch_window_clear_atomic(const Geo& g, const Bit
     return warp_sum_i(rad);
 }
 
+// neighbour lists of the thinning (patches whose windows intersect), built by the whole
+// GPU before the one-CTA rounds kernel: packed centres + fcmask rows, degrees, and (after an
+// exclusive scan of the degrees) the entries.  O(m^2) window tests spread over all SMs.
+__device__ __forceinline__ bool thin_overlap(const Geo& g, int a, int b)
+{
+    return abs((a >> 22) - (b >> 22)) < g.psz &&
+           abs(((a >> 11) & 2047) - ((b >> 11) & 2047)) < g.psy &&
+           abs((a & 2047) - (b & 2047)) < g.psx;
+}
+
+__global__ void thin_centres_kernel(const int32_t* __restrict__ sel, int m,
+                                    const int32_t* __restrict__ fgidx, ppp_cfg cfg,
+                                    int32_t* __restrict__ ctr, int32_t* __restrict__ row)
+{
+    Geo g = make_geo(cfg);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int vc = sel[i], z, y, x;
+    vox_decode(g, vc, z, y, x);
+    ctr[i] = (z << 22) | (y << 11) | x;
+    row[i] = fgidx[vc];
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+thin_neighbours_kernel(const int32_t* __restrict__ ctr, int m, ppp_cfg cfg,
+                       int32_t* __restrict__ deg, const int32_t* __restrict__ off,
+                       int32_t* __restrict__ nbr, int64_t cap)
+{
+    Geo g = make_geo(cfg);
+    __shared__ int s_c[128];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pi = i < m ? ctr[i] : 0;
+    int d = 0;
+    int64_t o = 0;
+    if (FILL) { if (off[m] > cap) return; o = i < m ? off[i] : 0; }      // lists disabled
+    for (int j0 = 0; j0 < m; j0 += 128) {
+        __syncthreads();
+        s_c[threadIdx.x] = j0 + threadIdx.x < m ? ctr[j0 + threadIdx.x] : 0;
+        __syncthreads();
+        const int nj = min(128, m - j0);
+        if (i < m)
+            for (int q = 0; q < nj; q++) {
+                const int j = j0 + q;
+                if (j != i && thin_overlap(g, pi, s_c[q])) {
+                    if (FILL) nbr[o + d] = j;
+                    d++;
+                }
+            }
+    }
+    if (!FILL && i < m) deg[i] = d;
+}
+
 #define THIN_LIST 2048      // per-round lists kept in shared memory
 #define THIN_DEG 64         // neighbour-list budget per patch (average); beyond: brute force
 
@@ -581,7 +635,6 @@ thin_rounds_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__
     __shared__ int s_remaining, s_total, s_nnew, s_nrec, s_go, s_cutc, s_cuti, s_nsel, s_lists;
     __shared__ int s_new[THIN_LIST];               // patches selected in this round
     __shared__ int s_rec[THIN_LIST];               // patches to count again / selected so far
-    __shared__ int s_scan[THIN_THREADS / 32];
     const int m = (int)m64;
     // per-patch state (global scratch): count, packed centre, fcmask row, count at
     // selection (-1: not selected), voxels newly removed from the radslice, round of
@@ -593,7 +646,8 @@ thin_rounds_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__
     int32_t* rcl = csel + m;
     int32_t* rnd = rcl + m;
     int32_t* off = rnd + m;                        // [m + 1]
-    int32_t* nbr = off + m + 1;                    // [<= THIN_DEG * m]
+    int32_t* hist = off + m + 1;                   // [P + 1] removed voxels per selection count
+    int32_t* nbr = hist + g.P + 1;                 // [<= THIN_DEG * m]
     BitVol bv;
     bv.WX = bitvol_wx(g.X);
     bv.w = use_smem ? s_bits : gbits;
@@ -601,11 +655,7 @@ thin_rounds_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__
     if (tid == 0) { s_remaining = 0; s_cutc = -1; s_cuti = -1; }
     __syncthreads();
     bitvol_init(g, bv, mask, &s_remaining);
-    for (int i = tid; i < m; i += THIN_THREADS) {
-        int vc = sel[i], z, y, x;
-        vox_decode(g, vc, z, y, x);
-        ctr[i] = (z << 22) | (y << 11) | x;
-        row[i] = fgidx[vc];
+    for (int i = tid; i < m; i += THIN_THREADS) {        // ctr / row / off / nbr: pre-kernels
         csel[i] = -1;
         rcl[i] = 0;
         rnd[i] = -1;
@@ -621,44 +671,10 @@ thin_rounds_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__
                                           (c >> 11) & 2047, c & 2047, lane, nullptr);
         if (lane == 0) cnt[i] = n;
     }
-    auto overlap = [&](int a, int b) {
-        return abs((a >> 22) - (b >> 22)) < g.psz &&
-               abs(((a >> 11) & 2047) - ((b >> 11) & 2047)) < g.psy &&
-               abs((a & 2047) - (b & 2047)) < g.psx;
-    };
-    // ---- neighbour lists (once): degree, exclusive scan, fill --------------------------
-    int carry = 0;
-    for (int base = 0; base < m; base += THIN_THREADS) {
-        const int i = base + tid;
-        int d = 0;
-        if (i < m) {
-            const int pi = ctr[i];
-            for (int j = 0; j < m; j++) d += (j != i && overlap(pi, ctr[j])) ? 1 : 0;
-        }
-        int incl = d;                              // block-wide exclusive scan of d
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) s_scan[w] = incl;
-        __syncthreads();
-        int wbase = 0, tot = 0;
-        for (int q = 0; q < nw; q++) { if (q < w) wbase += s_scan[q]; tot += s_scan[q]; }
-        if (i < m) off[i] = carry + wbase + incl - d;
-        carry += tot;
-        __syncthreads();
-    }
-    if (tid == 0) { off[m] = carry; s_lists = carry <= THIN_DEG * m; }
+    auto overlap = [&](int a, int b) { return thin_overlap(g, a, b); };
+    if (tid == 0) s_lists = off[m] <= (int64_t)THIN_DEG * m;
     __syncthreads();
     const bool lists = s_lists != 0;
-    if (lists)
-        for (int i = tid; i < m; i += THIN_THREADS) {
-            const int pi = ctr[i];
-            int o = off[i];
-            for (int j = 0; j < m; j++)
-                if (j != i && overlap(pi, ctr[j])) nbr[o++] = j;
-        }
-    __syncthreads();
     int round = 0;
     while (true) {
         // ---- 1. local maxima among the live patches ----------------------------------
@@ -739,45 +755,31 @@ thin_rounds_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__
         __syncthreads();
         // ---- 4. can the run already be cut? ---------------------------------------------
         if (s_remaining > 0) continue;             // the radslice is not empty yet
-        // position where the serial run stops: first patch (in selection order) at which
-        // the removed radslice voxels add up to the initial content.  The selected
-        // patches are gathered into shared memory first (s_rec is free here).
+        // position where the serial run stops: first patch (in selection order = count at
+        // selection descending, index ascending) at which the removed radslice voxels add up
+        // to the initial content.  Histogram of the removed voxels over the counts, a scan
+        // from the largest count down, then the order inside the one count where it crosses.
         if (tid == 0) { s_cutc = -1; s_cuti = 0x7fffffff; s_go = 0; s_nsel = 0; }
+        for (int c = tid; c <= g.P; c += THIN_THREADS) hist[c] = 0;
         __syncthreads();
         for (int i = tid; i < m; i += THIN_THREADS)
-            if (csel[i] >= 0) {
-                int k = atomicAdd(&s_nsel, 1);
-                if (k < THIN_LIST) s_rec[k] = i;
-            }
+            if (csel[i] >= 0) atomicAdd(&hist[csel[i]], rcl[i]);
         __syncthreads();
         const int total = s_total;
-        const int nsel = s_nsel;
-        const bool gathered = nsel <= THIN_LIST;
-        auto removed_upto = [&](int i, int ci) {   // voxels removed up to and including i
-            int acc = 0;
-            if (gathered) {
-                for (int k = 0; k < nsel; k++) {
-                    const int j = s_rec[k], cj = csel[j];
-                    if (j == i || thin_better(cj, j, ci, i)) acc += rcl[j];
-                }
-            } else {
-                for (int j = 0; j < m; j++) {
-                    const int cj = csel[j];
-                    if (cj >= 0 && (j == i || thin_better(cj, j, ci, i))) acc += rcl[j];
-                }
-            }
-            return acc;
-        };
-        const int nloop = gathered ? nsel : m;
-        for (int k = tid; k < nloop; k += THIN_THREADS) {
-            const int i = gathered ? s_rec[k] : k, ci = csel[i];
-            if (ci >= 0 && removed_upto(i, ci) >= total) atomicMax(&s_cutc, ci);
+        if (tid == 0) {
+            int acc = 0, c = g.P;
+            for (; c >= 0; c--) { if (acc + hist[c] >= total) break; acc += hist[c]; }
+            s_cutc = c;                            // -1: not reached (cannot happen here)
+            s_nsel = acc;                          // voxels removed by all larger counts
         }
         __syncthreads();
-        const int cutc = s_cutc;                   // count of the patch at the cut
-        for (int k = tid; k < nloop; k += THIN_THREADS) {
-            const int i = gathered ? s_rec[k] : k, ci = csel[i];
-            if (ci == cutc && removed_upto(i, ci) >= total) atomicMin(&s_cuti, i);
+        const int cutc = s_cutc, before = s_nsel;
+        for (int i = tid; i < m; i += THIN_THREADS) {
+            if (csel[i] != cutc) continue;
+            int acc = before;
+            for (int j = 0; j <= i; j++)
+                if (csel[j] == cutc) acc += rcl[j];
+            if (acc >= total) atomicMin(&s_cuti, i);
         }
         __syncthreads();
         const int cuti = s_cuti;
@@ -797,10 +799,21 @@ thin_rounds_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__
     }
 }
 
+static size_t thin_scan_bytes(int64_t m)
+{
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum((void*)nullptr, tb, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                  (int)(m > 0 ? m + 1 : 1));
+    return ((tb + 255) / 256) * 256 + 256;
+}
+
 extern "C" int64_t ppp_thin_scratch_bytes(const ppp_cfg* cfg, int64_t m)
 {
-    // bit volume + per-patch state (6 ints + offset) + neighbour lists (THIN_DEG per patch)
-    return ppp_cover_scratch_bytes(cfg) + 512 + (28 + 4 * THIN_DEG) * (m > 0 ? m : 0);
+    // bit volume + per-patch state (6 ints + offset) + histogram + degrees + scan temp +
+    // neighbour lists (THIN_DEG per patch)
+    Geo g = make_geo(*cfg);
+    return ppp_cover_scratch_bytes(cfg) + 4096 + 4 * ((int64_t)g.P + 1) +
+           (36 + 4 * THIN_DEG) * (m > 0 ? m : 0) + (int64_t)thin_scan_bytes(m);
 }
 
 extern "C" int ppp_thin(const uint8_t* mask, const int32_t* sel, int64_t m,
@@ -829,7 +842,33 @@ extern "C" int ppp_thin(const uint8_t* mask, const int32_t* sel, int64_t m,
                                                  SMEM_BITVOL_MAX);
             if (e != cudaSuccess) return ppp_fail((int)e, "ppp_thin: smem attribute");
         }
-        thin_rounds_kernel<<<1, THIN_THREADS, smem, (cudaStream_t)stream>>>(
+        // per-patch state, then histogram, neighbour lists, degrees, scan temp (layout shared
+        // with thin_rounds_kernel)
+        cudaStream_t st = (cudaStream_t)stream;
+        const int mi = (int)m;
+        int32_t* ctr = gcounts + m;
+        int32_t* row = gcounts + 2 * m;
+        int32_t* off = gcounts + 6 * m;
+        int32_t* hist = off + m + 1;
+        int32_t* nbr = hist + g.P + 1;
+        const int64_t cap = (int64_t)THIN_DEG * m;
+        int32_t* deg = nbr + cap;
+        void* scan_tmp = (void*)((((uintptr_t)(deg + m + 1)) + 255) / 256 * 256);
+        size_t stb = thin_scan_bytes(m);
+        thin_centres_kernel<<<(mi + 255) / 256, 256, 0, st>>>(sel, mi, fgidx, *cfg, ctr, row);
+        const int64_t maxdeg = (int64_t)(2 * g.psz - 1) * (2 * g.psy - 1) * (2 * g.psx - 1);
+        if ((maxdeg < m ? maxdeg : m) * m < 0x7fffffffLL) {
+            thin_neighbours_kernel<false><<<(mi + 127) / 128, 128, 0, st>>>(ctr, mi, *cfg, deg,
+                                                                             nullptr, nullptr, 0);
+            cudaMemsetAsync(deg + m, 0, 4, st);
+            cub::DeviceScan::ExclusiveSum(scan_tmp, stb, deg, off, mi + 1, st);
+            thin_neighbours_kernel<true><<<(mi + 127) / 128, 128, 0, st>>>(ctr, mi, *cfg, nullptr,
+                                                                            off, nbr, cap);
+        } else {
+            const int32_t big = 0x7fffffff;                       // lists off: brute force
+            cudaMemcpyAsync(off + m, &big, 4, cudaMemcpyHostToDevice, st);
+        }
+        thin_rounds_kernel<<<1, THIN_THREADS, smem, st>>>(
             mask, sel, m, fgidx, fcmask, *cfg, keep, gbits, gcounts, use_smem);
         return ppp_check("ppp_thin(rounds)");
     }
