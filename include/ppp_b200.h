@@ -189,6 +189,10 @@ int ppp_mws_host(const uint32_t* pairs, const float* aff, int64_t n,
  * inserting the tuples (pairs[i][0], pairs[i][1]) one by one -- what the reference
  * does with cKDTree.query_pairs' result.  pairs i64 [n][2], non-negative, distinct. */
 int ppp_pyset_order(const int64_t* pairs, int64_t n, int64_t* order);
+/* same, followed by the reference's distance filter (aff_patch_graph.py:61-69: drop a pair if
+ * |pts[i][d] - pts[j][d]| > thr[d] on any axis); out i64 [<= n][2] in set order, *n_out kept. */
+int ppp_pyset_pairs(const int64_t* pairs, int64_t n, const uint32_t* pts, const double* thr,
+                    int64_t* out, int64_t* n_out);
 
 /* instances i32 [V] (zeroed by the caller): for every node with comp > 0,
  * window pixels with pred > pt_gt take max(comp) ("later components overwrite

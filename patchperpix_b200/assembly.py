@@ -56,6 +56,29 @@ def query_pairs_set_order(tree, r):
     return np.array(list(pairs), dtype=np.int64).reshape(-1, 2)
 
 
+def query_pairs_filtered(tree, pts, r, thr):
+    """query_pairs_set_order followed by the reference's per-axis distance filter
+    (aff_patch_graph.py:61-69), in one pass on the host side of the library.
+    pts u32 [m,3], thr float [3]; returns int64 [k,2]."""
+    if _pyset_replay_ok():
+        import ctypes
+        a = np.ascontiguousarray(tree.query_pairs(r, p=1, output_type='ndarray'), np.int64)
+        if len(a) == 0:
+            return a.reshape(0, 2)
+        pts = np.ascontiguousarray(pts, np.uint32)
+        thr = np.ascontiguousarray(thr, np.float64)
+        out = np.empty((len(a), 2), np.int64)
+        n_out = ctypes.c_int64(0)
+        cc.call('ppp_pyset_pairs', a.ctypes.data, len(a), pts.ctypes.data, thr.ctypes.data,
+                out.ctypes.data, ctypes.addressof(n_out))
+        return out[:int(n_out.value)]
+    pa = query_pairs_set_order(tree, r)
+    if len(pa) == 0:
+        return pa
+    d = np.abs(pts[pa[:, 0]].astype(np.float32) - pts[pa[:, 1]].astype(np.float32))
+    return pa[~np.any(d > thr, axis=1)]
+
+
 def mutex_watershed(pairs, aff, cfg):
     """graph_mws.mws on the graph of setAffgraph (graph_mws.py:7-85,
     aff_patch_graph.py:31-40) through ppp_mws_host: the one serial graph pass of
@@ -256,14 +279,9 @@ class BlockAssembler:
         ordr = np.argsort(sel_coords[:, 2], kind='stable')       # :45
         pts = sel_coords[ordr].astype(np.uint32)
         tree = scipy.spatial.cKDTree(pts, leafsize=4)
-        pa = query_pairs_set_order(tree, 2 * np.sum(ps))         # :57
         max_ps = kw.get("max_total_patch_distance_in_ps_multiples", 2)
-        if len(pa):
-            d = np.abs(pts[pa[:, 0]].astype(np.float32) - pts[pa[:, 1]].astype(np.float32))
-            keep = ~np.any(d > max_ps * ps, axis=1)              # :61-69
-            pa = pa[keep]
-        else:
-            pa = np.zeros((0, 2), np.int64)
+        pa = query_pairs_filtered(tree, pts, 2 * np.sum(ps),     # :57, :61-69
+                                  np.asarray(max_ps * ps, np.float64))
         single = bool(kw.get('includeSinglePatchCCS', False))
         total = len(pa) + (m if single else 0)
         if total == 0:

@@ -245,3 +245,38 @@ extern "C" int ppp_pyset_order(const int64_t* pairs, int64_t n, int64_t* order)
         if (set.slot[s] >= 0) order[out++] = set.slot[s];
     return out == n ? 0 : ppp_fail(-1, "ppp_pyset_order: internal error");
 }
+
+// same replay, followed by the reference's distance filter (aff_patch_graph.py:61-69:
+// a pair is dropped if |delta_d| > thr[d] on any axis), written out in set order:
+// out i64 [<= n][2], *n_out pairs kept.  pts u32 [m][3] (the points the indices refer to).
+extern "C" int ppp_pyset_pairs(const int64_t* pairs, int64_t n, const uint32_t* pts,
+                               const double* thr, int64_t* out, int64_t* n_out)
+{
+    if (!n_out || n < 0 || (n > 0 && (!pairs || !pts || !thr || !out)))
+        return ppp_fail(-1, "ppp_pyset_pairs: null argument");
+    std::vector<uint64_t> h((size_t)n);
+    for (int64_t k = 0; k < n; k++) {
+        if (pairs[2 * k] < 0 || pairs[2 * k + 1] < 0)
+            return ppp_fail(-1, "ppp_pyset_pairs: negative index");
+        h[k] = py_tuple2_hash((uint64_t)pairs[2 * k], (uint64_t)pairs[2 * k + 1]);
+    }
+    PySetReplay set(h);
+    for (int64_t k = 0; k < n; k++) set.add(k);
+    int64_t kept = 0;
+    for (size_t s = 0; s <= set.mask; s++) {
+        const int64_t k = set.slot[s];
+        if (k < 0) continue;
+        const int64_t i = pairs[2 * k], j = pairs[2 * k + 1];
+        bool drop = false;
+        for (int d = 0; d < 3; d++) {
+            const double delta = (double)pts[3 * i + d] - (double)pts[3 * j + d];
+            if ((delta < 0 ? -delta : delta) > thr[d]) drop = true;
+        }
+        if (drop) continue;
+        out[2 * kept] = i;
+        out[2 * kept + 1] = j;
+        kept++;
+    }
+    *n_out = kept;
+    return 0;
+}

@@ -124,6 +124,7 @@ _SIGS = {
     'ppp_label_cc': (ctypes.c_int, ['p', 'p', 'i64', 'cfg', 'p', 'p', 'p', 'p']),
     'ppp_mws_host': (ctypes.c_int, ['p', 'p', 'i64', 'cfg', 'p', 'p', 'p', 'p']),
     'ppp_pyset_order': (ctypes.c_int, ['p', 'i64', 'p']),
+    'ppp_pyset_pairs': (ctypes.c_int, ['p', 'i64', 'p', 'p', 'p', 'p']),
     'ppp_paint': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
     'ppp_paint_channels': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
     'ppp_paint_patches': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),

@@ -111,3 +111,22 @@ def test_query_pairs_set_order_equals_python_set():
     for r in (4, 21, 42):
         want = np.array(list(tree.query_pairs(r, p=1)), np.int64).reshape(-1, 2)
         assert np.array_equal(query_pairs_set_order(tree, r), want)
+
+
+def test_query_pairs_filtered_equals_reference_loop():
+    """set order + per-axis distance filter in one library call == the reference's
+    remove-from-the-set loop (aff_patch_graph.py:57-69)."""
+    import scipy.spatial
+    from patchperpix_b200.assembly import query_pairs_filtered
+    rng = np.random.default_rng(5)
+    ps = np.array([3, 7, 5])
+    pts = rng.integers(0, 60, (900, 3)).astype(np.uint32)
+    pts = pts[np.argsort(pts[:, 2], kind='stable')]
+    tree = scipy.spatial.cKDTree(pts, leafsize=4)
+    pairs = tree.query_pairs(2 * np.sum(ps), p=1)
+    for p in list(pairs):
+        if np.any(np.abs(pts[p[0]].astype(np.float32) - pts[p[1]].astype(np.float32)) > 2 * ps):
+            pairs.remove(p)
+    want = np.array(list(pairs), np.int64).reshape(-1, 2)
+    got = query_pairs_filtered(tree, pts, 2 * np.sum(ps), np.asarray(2 * ps, np.float64))
+    assert np.array_equal(got, want)
