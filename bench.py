@@ -48,7 +48,7 @@ KW = dict(patch_threshold=0.5, fc_threshold=0.5, cuda=True, blockwise=False,
           overlapping_inst=True, skipThinCover=False)
 # kernels launched per C-ABI call (counted to report gpu_launches)
 # (own kernels + the CUB radix-sort passes the library launches; checked against
-# the ncu launch list profiles/r1_v9_launches.csv: 46 per step)
+# the ncu launch list profiles/r1_v10_launches.csv: 51 per step)
 LAUNCHES = dict(ppp_gate=1, ppp_compact=3, ppp_prepare_patches=2, ppp_consensus=3,
                 ppp_rank=10, ppp_rank_sort=12, ppp_cover=4, ppp_thin=6, ppp_patch_graph=1,
                 ppp_label_cc=8, ppp_paint=1)
