@@ -263,7 +263,8 @@ def main():
 
     ps = np.array(WORKLOAD['patchshape'])
     _, P, _, _, _, K = patch_geometry(ps)
-    pred, numinst, _ = make_inputs(dev, WORKLOAD['seed'] + rank)
+    # every rank assembles its own copy of the SAME image: equal work per GPU (weak scaling)
+    pred, numinst, _ = make_inputs(dev, WORKLOAD['seed'])
     mid = P // 2
     fg = (pred[mid] > 0.5).to(torch.uint8)
     overlap = torch.from_numpy((numinst > 1).astype(np.uint8)).to(dev)

@@ -196,6 +196,20 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
             _unpad(fg).cpu().numpy().astype(np.uint8))
 
 
+_STREAM_CACHE = {}
+
+
+def _cached_stream(dev_index, name):
+    """side streams are created once per device and role: torch's caching allocator
+    keeps one memory pool per stream, a fresh stream per call would re-allocate
+    (cudaMalloc) several GB of working buffers every time (~150 ms on the bench image)."""
+    import torch
+    key = (dev_index, name)
+    if key not in _STREAM_CACHE:
+        _STREAM_CACHE[key] = torch.cuda.Stream(torch.device('cuda', dev_index))
+    return _STREAM_CACHE[key]
+
+
 def to_instance_seg_stream(samples, patchshape, workers=1, **kwargs):
     """Assemble a sequence of samples as a pipeline (the reference handles them
     strictly one after the other, run_ppp.py:1111-1190, vote_instances.py:586-605):
@@ -216,7 +230,7 @@ def to_instance_seg_stream(samples, patchshape, workers=1, **kwargs):
     import torch
     dev_index = torch.cuda.current_device()
     dev = torch.device('cuda', dev_index)
-    copy = torch.cuda.Stream(dev)
+    copy = _cached_stream(dev_index, 'copy')
     workers = max(1, int(workers))
     nslots = workers + 1
     bufs = [None] * nslots             # device copies of the samples in flight
@@ -245,10 +259,14 @@ def to_instance_seg_stream(samples, patchshape, workers=1, **kwargs):
         bufs[slot] = devt
         return ready
 
+    free_streams = [_cached_stream(dev_index, 'worker%d' % k) for k in range(workers)]
+    lock = threading.Lock()
+
     def assemble(slot, ready):
         torch.cuda.set_device(dev_index)
         if not hasattr(local, 'stream'):
-            local.stream = torch.cuda.Stream(dev)
+            with lock:
+                local.stream = free_streams.pop()
         with torch.cuda.stream(local.stream):
             local.stream.wait_event(ready)
             pred, fg, mask, numinst = bufs[slot]
