@@ -171,8 +171,14 @@ def run_reference_arm(args):
     y0, x0 = (pred.shape[2] - Y) // 2, (pred.shape[3] - X) // 2
     crop = np.ascontiguousarray(pred[:, :, y0:y0 + Y, x0:x0 + X])
     ncrop = np.ascontiguousarray(numinst[:, y0:y0 + Y, x0:x0 + X])
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     cores = os.cpu_count()
-    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    os.environ['OMP_NUM_THREADS'] = str(cores)
+    try:
+        import ctypes
+        ctypes.CDLL('libgomp.so.1').omp_set_num_threads(int(cores))
+    except OSError:
+        pass
     times = []
     nfg = 0
     for i in range(args.warmup + args.steps):
