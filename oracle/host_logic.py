@@ -181,8 +181,30 @@ def mutex_watershed(g):
     return [[names[i] for i in member[c]] for c in member if c > 0]
 
 
+def pack_no_overlap(channels, shape, dtype, min_size=2000):
+    """graph_to_labeling.py:96-113 (no_overlap_per_channel): instances larger than
+    `min_size` voxels go to the first channel where their voxels are all free, else
+    to a new channel; smaller ones are written into channel 0 (overwriting)."""
+    out = []
+    for k, cur in enumerate(channels):
+        if not out:
+            out.append(cur.copy())
+            continue
+        m = cur > 0
+        if np.sum(m) > min_size:
+            for ch in out:
+                if np.all(ch[m] == 0):
+                    ch[m] = k + 1
+                    break
+            else:
+                out.append(cur.copy())
+        else:
+            out[0][m] = k + 1
+    return np.stack(out, axis=0) if out else np.zeros((0,) + tuple(shape), dtype)
+
+
 def label_instances(pairs, aff, pred, patchshape, rad, shape, patch_threshold,
-                    dtype=np.uint16, mws=False, per_channel=False):
+                    dtype=np.uint16, mws=False, per_channel=False, no_overlap=False):
     """aff_patch_graph.py:31-40 + graph_to_labeling.py:44-84; per_channel =
     one_instance_per_channel (:57-95, 114-115): every component painted into its
     own volume, stacked."""
@@ -200,15 +222,17 @@ def label_instances(pairs, aff, pred, patchshape, rad, shape, patch_threshold,
     ccs = mutex_watershed(g) if mws else nx.connected_components(pos)
     for k, cc in enumerate(ccs):
         comps.append(sorted(cc))
-        target = np.zeros(shape, dtype) if per_channel else inst
+        target = np.zeros(shape, dtype) if (per_channel or no_overlap) else inst
         for idx in cc:
             idx = np.array(idx)
             patch = pred[(slice(None),) + tuple(idx)].reshape(patchshape)
             sl = _window(idx, rad)
             target[sl][patch > patch_threshold] = k + 1
-        if per_channel:
+        if per_channel or no_overlap:
             channels.append(target)
-    if per_channel:
+    if no_overlap:
+        inst = pack_no_overlap(channels, shape, dtype)
+    elif per_channel:
         inst = np.stack(channels, axis=0) if channels else np.zeros((0,) + tuple(shape), dtype)
     return inst, comps
 
@@ -247,7 +271,8 @@ def assemble(pred, foreground, numinst, patchshape, kw, kern):
     inst, comps = label_instances(pairs, aff, pred, ps, rad, foreground.shape,
                                   np.float32(kw['patch_threshold']),
                                   mws=kw.get('mws', False),
-                                  per_channel=kw.get('one_instance_per_channel', False))
+                                  per_channel=kw.get('one_instance_per_channel', False),
+                                  no_overlap=kw.get('no_overlap_per_channel', False))
     out['instances'] = inst
     out['components'] = comps
     return out

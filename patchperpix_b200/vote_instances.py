@@ -25,7 +25,7 @@ logger = logging.getLogger(__name__)
 
 _UNSUPPORTED = ('isbiHack', 'debug', 'graphToInst', 'use_score_oracle',
                 'mark_close_neighboorhood', 'select_patches_overlap_neighborhood',
-                'thin_cover_use_kd', 'no_overlap_per_channel', 'shuffle_patches')
+                'thin_cover_use_kd', 'shuffle_patches')
 
 
 def merge_dicts(sink, source):
@@ -52,6 +52,33 @@ def _to_device(a, dtype=None):
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t.contiguous()
+
+
+def pack_no_overlap_channels(stack, min_size=2000):
+    """no_overlap_per_channel (graph_to_labeling.py:96-113) on the device: `stack` i32
+    [n_comp,Z,Y,X] = one channel per component (ppp_paint_channels).  Components larger
+    than `min_size` voxels go to the first channel where their voxels are all free, else
+    they open a new channel; smaller ones are written into channel 0 (overwriting)."""
+    import torch
+    out = []
+    for k in range(int(stack.shape[0])):
+        cur = stack[k]
+        if not out:
+            out.append(cur.clone())
+            continue
+        m = cur > 0
+        if int(m.sum().item()) > min_size:
+            for ch in out:
+                if not bool((ch[m] != 0).any().item()):
+                    ch[m] = k + 1
+                    break
+            else:
+                out.append(cur.clone())
+        else:
+            out[0][m] = k + 1
+    if not out:
+        return stack[:0]
+    return torch.stack(out, dim=0)
 
 
 def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
@@ -183,11 +210,14 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
         (pairs[:, 0].astype(np.int64) * Y + pairs[:, 1]) * X + pairs[:, 2],
         (pairs[:, 3].astype(np.int64) * Y + pairs[:, 4]) * X + pairs[:, 5]]))
     nodes = torch.from_numpy(nodes_np.astype(np.int32)).to(pred.device)
-    per_channel = bool(kwargs.get('one_instance_per_channel', False))
+    no_overlap = bool(kwargs.get('no_overlap_per_channel', False))
+    per_channel = bool(kwargs.get('one_instance_per_channel', False)) or no_overlap
     inst, ncomp = asm.label(pairs_dev, aff, nodes, mws=kwargs.get('mws', False),
                             per_channel=per_channel)
     if ncomp > 65535:
         logger.warning("%d components do not fit the reference's uint16 labels", ncomp)
+    if no_overlap:
+        inst = pack_no_overlap_channels(inst)
     if per_channel:                                            # graph_to_labeling.py:143-151
         inst = inst[(slice(None),) + radslice] if kwargs.get("pad_with_ps", False) else inst
     else:
@@ -324,7 +354,8 @@ def do_all(aff_file, patchshape=np.array([1, 25, 25]), **kwargs):
         return
     foreground = foreground.astype(np.uint8)
     if kwargs.get('crop_to_foreground', True):                 # :535-540
-        if kwargs.get('one_instance_per_channel', False):
+        if kwargs.get('one_instance_per_channel', False) or \
+                kwargs.get('no_overlap_per_channel', False):
             instances[:, foreground == 0] = 0
         else:
             instances[foreground == 0] = 0

@@ -12,7 +12,7 @@ from patchperpix_b200 import synth
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 NAMES = sorted(os.path.basename(f)[:-4]
                for f in glob.glob(os.path.join(GOLD, '*.npz'))
-               if not os.path.basename(f).startswith(('blockwise', 'mws_')))
+               if not os.path.basename(f).startswith(('blockwise', 'mws_', 'chan_')))
 _TUPLES = ('shape', 'width', 'length', 'radius', 'rad_xy', 'rad_z', 'centers')
 
 

@@ -123,3 +123,48 @@ def test_gpu_one_instance_per_channel(name, tag):
     want = _opc_expected(tag, name)
     assert stack.dtype == np.uint16 and stack.shape == want.shape
     assert np.array_equal(stack, want)
+
+
+# ---------------------------------------------------------------------------
+# no_overlap_per_channel (graph_to_labeling.py:96-113)
+# ---------------------------------------------------------------------------
+def _no_overlap_case():
+    import hashlib
+    import json
+    sys_path_tools = os.path.join(os.path.dirname(golden_util.GOLD), '..', 'tools')
+    g = dict(np.load(os.path.join(golden_util.GOLD, 'chan_nooverlap2d_ps9.npz')))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        'gen_golden_case', os.path.join(os.path.abspath(sys_path_tools), 'no_overlap_case.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    pred, numinst, _ = mod.no_overlap_case()
+    assert hashlib.sha1(pred.astype(np.float16).tobytes()).hexdigest() == str(g['pred_sha1'])
+    assert np.array_equal(numinst, g['numinst'])
+    return g, json.loads(str(g['kwargs'])), pred, numinst
+
+
+@pytest.mark.parametrize('tag', ['cc', 'mws'])
+def test_oracle_no_overlap_per_channel(tag):
+    from oracle import cpu_oracle, host_logic
+    g, kw, pred, numinst = _no_overlap_case()
+    ps = np.array([1, 9, 9])
+    kw = dict(kw, mws=(tag == 'mws'))
+    fg = pred[40] > np.float32(kw['patch_threshold'])
+    O = cpu_oracle.Oracle(pred, numinst > 1, ps, cpu_oracle.variant_from_kwargs(kw))
+    out = host_logic.assemble(pred, fg, numinst, ps, kw, O)
+    assert out['instances'].shape[0] == 2
+    assert np.array_equal(out['instances'], g['stack_' + tag])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', ['cc', 'mws'])
+def test_gpu_no_overlap_per_channel(tag):
+    from patchperpix_b200 import vote_instances as vi
+    g, kw, pred, numinst = _no_overlap_case()
+    ps = np.array([1, 9, 9])
+    kw = dict(kw, mws=(tag == 'mws'))
+    fg = pred[40] > np.float32(kw['patch_threshold'])
+    stack, _ = vi.to_instance_seg(pred.copy(), fg.copy(), fg.copy(), numinst.copy(), ps.copy(), **kw)
+    assert stack.dtype == np.uint16
+    assert np.array_equal(stack, g['stack_' + tag])

@@ -22,6 +22,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 from oracle import ref_runner            # noqa: E402
 from patchperpix_b200 import synth, layout  # noqa: E402
 
@@ -327,7 +328,40 @@ def run_mws(S):
     print('mws_cases %.2f MB' % (os.path.getsize(fn) / 1e6))
 
 
+from no_overlap_case import no_overlap_case  # noqa: E402
+
+
+def run_no_overlap(S):
+    """no_overlap_per_channel (graph_to_labeling.py:96-113): instances larger than 2000
+    voxels go to the first channel they do not overlap, smaller ones into channel 0.
+    Four big overlapping discs and a small one through the reference's to_instance_seg."""
+    import hashlib
+    ps = np.array([1, 9, 9])
+    pred, numinst, labels = no_overlap_case()
+    kw = S.default_kwargs(no_overlap_per_channel=True)
+    fg = pred[40] > kw['patch_threshold']
+    res = {}
+    for tag, use_mws in (('cc', False), ('mws', True)):
+        k2 = dict(kw, mws=use_mws)
+        stack, _ = S.vi.to_instance_seg(pred.copy(), fg.copy(), fg.copy(), numinst.copy(),
+                                        ps.copy(), **k2)
+        stack = np.asarray(stack)
+        res['stack_' + tag] = stack.astype(np.uint16)
+        print('no_overlap %s: channels %d, labels %s' % (tag, stack.shape[0],
+                                                        [np.unique(c).tolist() for c in stack]))
+    res['pred_sha1'] = hashlib.sha1(pred.astype(np.float16).tobytes()).hexdigest()
+    res['numinst'] = numinst
+    res['kwargs'] = json.dumps({k: v for k, v in kw.items()
+                                if isinstance(v, (bool, int, float, str))})
+    fn = os.path.join(GOLD, 'chan_nooverlap2d_ps9.npz')
+    np.savez_compressed(fn, **res)
+    print('chan_nooverlap2d_ps9 %.2f MB' % (os.path.getsize(fn) / 1e6))
+
+
 def main():
+    if sys.argv[1:] == ['nooverlap']:
+        run_no_overlap(ref_runner.RefSession())
+        return 0
     if sys.argv[1:] == ['mws']:
         run_mws(ref_runner.RefSession())
         return 0
