@@ -168,3 +168,25 @@ def test_gpu_no_overlap_per_channel(tag):
     stack, _ = vi.to_instance_seg(pred.copy(), fg.copy(), fg.copy(), numinst.copy(), ps.copy(), **kw)
     assert stack.dtype == np.uint16
     assert np.array_equal(stack, g['stack_' + tag])
+
+
+def test_channel_packing_matches_oracle_on_random_stacks():
+    """vote_instances.pack_no_overlap_channels (torch ops, device-agnostic) against the
+    oracle's restatement on random instance stacks with a small size threshold."""
+    import torch
+    from oracle import host_logic
+    from patchperpix_b200.vote_instances import pack_no_overlap_channels
+    rng = np.random.default_rng(8)
+    for trial in range(20):
+        n = int(rng.integers(1, 9))
+        stack = np.zeros((n, 1, 24, 24), np.int32)
+        for k in range(n):
+            if rng.random() < 0.15:
+                continue                                  # empty component (mws id gap)
+            y, x = rng.integers(0, 16, 2)
+            h, w = rng.integers(2, 9, 2)
+            stack[k, 0, y:y + h, x:x + w] = k + 1
+        want = host_logic.pack_no_overlap([c.copy() for c in stack], stack.shape[1:], np.int32,
+                                          min_size=20)
+        got = pack_no_overlap_channels(torch.from_numpy(stack), min_size=20).numpy()
+        assert np.array_equal(got, want), trial
