@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(kind='worms', shape=(520, 696), patchshape=(1, 41, 41), seed=2,
                 n_worms=40)
-CPU_SAMPLE = (1, 160, 160)      # crop the CPU arm works on (prebuilt oracle/_ref shapes)
+CPU_SAMPLE = (1, 256, 256)      # crop the CPU arm works on (prebuilt oracle/_ref shapes)
 KW = dict(patch_threshold=0.5, fc_threshold=0.5, cuda=True, blockwise=False,
           select_patches_for_sparse_data=True, includeSinglePatchCCS=True, mws=False,
           consensus_norm_prob_product=True, consensus_prob_product=True,
