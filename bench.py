@@ -1,29 +1,33 @@
 #!/usr/bin/env python
 """bench.py — consensus+assembly foreground Mvoxels/s (BASELINE.json metric).
 
-Workload at N=1 = BASELINE.json configs[1]: 2-D BBBC010-style worm bodies,
-696x520, patchshape 1x41x41, synthetic seeded patch predictions
-(patchperpix_b200/synth.py), flylight [vote_instances] flags, thresholded CC.
-A "step" = the whole assembly path (gate -> consensus -> rank -> cover ->
-thin -> patch graph -> CC -> paint) over one image.
+Workload = BASELINE.json configs[4] (the north-star volume): ONE FlyLight-sized
+3-D volume, 256x1024x1024, patchshape 7x7x7, synthetic neurites (seeded,
+patchperpix_b200/synth.py), predictions in the compact row form a ppp+dec run
+produces (float16 [G][343] for the G foreground voxels), assembled BLOCKWISE
+(chunks 128^3 + patchshape//2 halo, one job per shared face, one global
+partition) through patchperpix_b200.sharded.stitch_shard.  flylight
+[vote_instances] flags, thresholded connected components.
 
-  value : fg voxels / s, inputs resident in HBM, CUDA-event timed
-  e2e   : same through patchperpix_b200.vote_instances.to_instance_seg_stream
-          with PINNED HOST inputs (float16, the stored form): every step copies
-          its own prediction H2D and reads its labels back inside the timed
-          region; the copy of sample i+1 overlaps the assembly of sample i.
-          serial_ms_per_step = one to_instance_seg call after the other.
-  roofline : the stage with the largest CUDA-event time (consensus or rank),
-             algorithmic bytes per fg voxel (consensus
-             P*4 + 1 + K*8, rank P*4 + K*4 + 4) vs MEASURED_PEAKS.json;
-             roofline_other = the other one
-  cpu_baseline : the reference kernels compiled for the host (oracle/_ref,
-             all cores) + the oracle host logic on a bounded crop
+N GPUs = the SAME volume cut into N slabs of whole block rows ("scaling": "strong");
+NCCL moves halo rows (send/recv), block and face edge lists (all-gather).  A "step"
+= the whole path over the whole volume: halo exchange -> per block gate/compact/
+prepare/consensus/rank/cover/thin/pairs/patch graph -> face jobs -> global CC ->
+painting of the own slab.
 
---impl reference runs only that CPU arm.  N>1 (torchrun): every rank
-assembles its own image (independent objects, no data-path collective; weak).
+  value : fg voxels of the volume / s, patch rows resident in HBM, CUDA-event timed
+  e2e   : same from PINNED HOST rows (H2D of coords+patches+numinst inside the
+          timed region) to uint16 labels of the own slab back on the host
+  roofline : the C-ABI call with the largest summed CUDA-event time over a step
+          (events around every call of one extra, single-stream pass), algorithmic
+          bytes per fg voxel of SURVEY.md 8d vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference : the reference kernels compiled for the host
+          (oracle/_ref, OpenMP, all cores) + the oracle host logic on a bounded
+          sample region of the same volume; the GPU path assembles the same
+          region and the labels are compared ("parity_checked")
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -36,22 +40,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(kind='worms', shape=(520, 696), patchshape=(1, 41, 41), seed=2,
-                n_worms=40)
-CPU_SAMPLE = (1, 256, 256)      # crop the CPU arm works on (prebuilt oracle/_ref shapes)
-KW = dict(patch_threshold=0.5, fc_threshold=0.5, cuda=True, blockwise=False,
+WORKLOAD = dict(shape=(256, 1024, 1024), patchshape=(7, 7, 7), chunksize=(128, 128, 128),
+                seed=4, n=600, seg_len=24.0, n_seg=40)
+CPU_SAMPLE = (72, 72, 72)       # region the CPU arm works on (prebuilt oracle/_ref shapes)
+KW = dict(patch_threshold=0.5, fc_threshold=0.5, cuda=True, blockwise=True,
           select_patches_for_sparse_data=True, includeSinglePatchCCS=True, mws=False,
           consensus_norm_prob_product=True, consensus_prob_product=True,
           consensus_norm_aff=True, consensus_interleaved_cnt=False,
           vi_bg_use_inv_th=False, vi_bg_use_half_th=False, vi_bg_use_less_than_th=True,
           rank_norm_patch_score=True, rank_int_counter=False, patch_graph_norm_aff=True,
           overlapping_inst=True, skipThinCover=False)
-# kernels launched per C-ABI call (counted to report gpu_launches)
-# (own kernels + the CUB radix-sort passes the library launches; checked against
-# the ncu launch list profiles/r1_v10_launches.csv: 51 per step)
-LAUNCHES = dict(ppp_gate=1, ppp_compact=3, ppp_prepare_patches=2, ppp_consensus=3,
-                ppp_rank=10, ppp_rank_sort=12, ppp_cover=4, ppp_thin=6, ppp_patch_graph=1,
-                ppp_label_cc=8, ppp_paint=1)
 
 
 def peaks():
@@ -99,20 +97,51 @@ class ClockSampler(threading.Thread):
                     samples=len(self.rows))
 
 
-def make_inputs(device, seed):
+def workload_from_args(args):
+    w = dict(WORKLOAD)
+    if args.shape:
+        w['shape'] = tuple(int(v) for v in args.shape.split(','))
+        w['n'] = max(4, int(WORKLOAD['n'] * np.prod(w['shape']) / np.prod(WORKLOAD['shape'])))
+    if args.chunk:
+        w['chunksize'] = tuple(int(v) for v in args.chunk.split(','))
+    return w
+
+
+def synth_kw(w):
+    return dict(seed=w['seed'], n=w['n'], seg_len=w['seg_len'], n_seg=w['n_seg'])
+
+
+# ---------------------------------------------------------------------------
+# the bounded sample both arms can afford: a region of the same volume
+# ---------------------------------------------------------------------------
+def sample_region(w):
+    """a CPU_SAMPLE-sized box of the volume around a neurite (deterministic)."""
     from patchperpix_b200 import synth
-    w = WORKLOAD
-    labels, numinst = synth.worms_2d(w['shape'], n_worms=w['n_worms'], seed=seed)
-    pred = synth.patches_from_labels(labels, w['patchshape'], seed=seed, device=device)
-    return pred, numinst, labels
+    shape = np.asarray(w['shape'])
+    size = np.minimum(np.asarray(CPU_SAMPLE), shape)
+    # first polyline point of the generator's random sequence that lies inside
+    rng = np.random.default_rng(w['seed'])
+    p = np.array([rng.uniform(0, shape[0]), rng.uniform(0, shape[1]), rng.uniform(0, shape[2])])
+    start = np.clip(p.astype(int) - size // 2, 0, shape - size)
+    # labels of a slab window around it, dense patches of the region
+    ps = w['patchshape']
+    lo, hi = int(start[0]), int(start[0] + size[0])
+    coords, patches, numinst = synth.neurite_rows(w['shape'], ps, axis=0, lo=lo, hi=hi,
+                                                  device='cpu', box=(start, start + size),
+                                                  **synth_kw(w))
+    c = coords.numpy().astype(np.int64) - start
+    P = int(np.prod(ps))
+    pred = np.zeros((P,) + tuple(int(s) for s in size), np.float32)
+    pred[:, c[:, 0], c[:, 1], c[:, 2]] = patches.numpy().astype(np.float32).T
+    ni = np.zeros(tuple(int(s) for s in size), np.uint8)
+    ni[c[:, 0], c[:, 1], c[:, 2]] = numinst.numpy()
+    return pred, ni, start
 
 
-# ---------------------------------------------------------------------------
-# reference arm: reference kernels on the host cores + oracle host logic
-# ---------------------------------------------------------------------------
 def cpu_reference_step(pred_np, numinst_np, ps, kw):
-    """one pass of the reference CPU arm over a crop; returns (#fg, seconds)."""
-    from oracle import ref_runner, host_logic, cpu_oracle
+    """one pass of the reference CPU arm over a region: reference kernels (host
+    build, OpenMP) + oracle host logic.  Returns (#fg, seconds, labels u16)."""
+    from oracle import ref_runner, host_logic
     dims = pred_np.shape[1:]
     base = ['-DUSE_LESS_THAN_TH', '-DOVERLAP']
     th = kw['patch_threshold']
@@ -148,6 +177,7 @@ def cpu_reference_step(pred_np, numinst_np, ps, kw):
     sel = host_logic.foreground_cover(1 * overlap, mask, np.array(ps), ranked, rad, pred_np, fc)
     sel = host_logic.thin_cover(mask, sel, np.array(ps), rad, pred_np, fc)
     pairs = host_logic.patch_pairs(sel, np.array(ps), True, 2)
+    inst = np.zeros(dims, np.uint16)
     if pairs is not None:
         aff = np.zeros(len(pairs), np.float32)
         n = len(pairs)
@@ -155,23 +185,14 @@ def cpu_reference_step(pred_np, numinst_np, ps, kw):
             nb = min(512, n - i)
             ks['graph'](pred_np, cons, aff, pairs, np.uint64(nb), np.int32(i),
                         block=(min(512, n), 1, 1), grid=((nb + min(512, n) - 1) // min(512, n), 1, 1))
-        host_logic.label_instances(pairs, aff, pred_np, np.array(ps), rad, dims,
-                                   np.float32(th))
+        inst, _ = host_logic.label_instances(pairs, aff, pred_np, np.array(ps), rad, dims,
+                                             np.float32(th))
     dt = time.perf_counter() - t0
-    return int(fg.sum()), dt
+    return int(fg.sum()), dt, inst
 
 
-def run_reference_arm(args):
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
-        return 0
-    ps = WORKLOAD['patchshape']
-    pred, numinst, _ = make_inputs(None, WORKLOAD['seed'])
-    Z, Y, X = CPU_SAMPLE
-    y0, x0 = (pred.shape[2] - Y) // 2, (pred.shape[3] - X) // 2
-    crop = np.ascontiguousarray(pred[:, :, y0:y0 + Y, x0:x0 + X])
-    ncrop = np.ascontiguousarray(numinst[:, y0:y0 + Y, x0:x0 + X])
-    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+def all_host_threads():
+    """use every host core, also under torchrun (which exports OMP_NUM_THREADS=1)."""
     cores = os.cpu_count()
     os.environ['OMP_NUM_THREADS'] = str(cores)
     try:
@@ -179,22 +200,37 @@ def run_reference_arm(args):
         ctypes.CDLL('libgomp.so.1').omp_set_num_threads(int(cores))
     except OSError:
         pass
+    return cores
+
+
+def workload_name(w):
+    return ('configs[4]: 3-D FlyLight-sized volume %dx%dx%d, patchshape 7x7x7, %d synthetic '
+            'neurites, compact f16 patch rows, blockwise chunks %s + halo, sharded in slabs'
+            % (w['shape'] + (w['n'],) + ('x'.join(str(c) for c in w['chunksize']),)))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    w = workload_from_args(args)
+    cores = all_host_threads()
+    pred, ni, start = sample_region(w)
     times = []
     nfg = 0
     for i in range(args.warmup + args.steps):
-        nfg, dt = cpu_reference_step(crop, ncrop, ps, KW)
+        nfg, dt, _ = cpu_reference_step(pred, ni, w['patchshape'], KW)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     val = nfg / (ms * 1e-3) / 1e6
-    sample = 'centre crop %dx%d of the %dx%d image (%d fg voxels), all stages' % (
-        Y, X, pred.shape[2], pred.shape[3], nfg)
+    sample = 'region %s at %s of the volume (%d fg voxels), all stages, single block' % (
+        'x'.join(str(s) for s in pred.shape[1:]), tuple(int(v) for v in start), nfg)
     line = dict(metric='consensus+assembly fg Mvoxels/s', value=val, unit='Mvoxels/s',
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
-                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32',
                 data='synthetic', impl='reference',
-                config=dict(workload='configs[1]: 2D worms 696x520, patchshape 1x41x41',
-                            sample=sample),
+                config=dict(workload=workload_name(w), sample=sample),
                 cpu_baseline=dict(value=val, unit='Mvoxels/s', cores=cores, kind='reference',
                                   sample=sample),
                 e2e=dict(value=val, unit='Mvoxels/s', h2d_bytes_per_step=0,
@@ -206,46 +242,66 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
-def device_step(pred, fg, overlap, mask, ps, kw, timers=None):
-    """the hot path on device-resident inputs; returns (labels tensor, F)."""
-    import torch
-    from patchperpix_b200.assembly import BlockAssembler
-    asm = BlockAssembler(pred, fg, overlap, ps, **kw)
-    asm.prepare()
-    if timers is not None:
-        timers[0].record()
-    asm.consensus(want_cnt=True)
-    if timers is not None:
-        timers[1].record()
-    asm.rank()
-    if timers is not None:
-        timers[2].record()
-    order = asm.ranked()
-    sel = asm.cover(mask, order)
-    sel = asm.thin(mask, sel)
-    pairs = asm.patch_pairs(asm.coords(sel))
-    if pairs is None:
-        return torch.zeros(asm.shape, dtype=torch.int32, device=pred.device), asm.F
-    pd = torch.from_numpy(pairs.view(np.int32)).to(pred.device)
-    aff = asm.patch_graph(pd)
-    inst, _ = asm.label(pd, aff, sel)
-    return inst, asm.F
+class CallTimer:
+    """CUDA events around every C-ABI call (single-stream profiling pass) and a
+    count of the rows each consensus / rank call processed."""
+
+    def __init__(self, cc, torch):
+        self.cc, self.torch = cc, torch
+        self.orig = cc.call
+        self.ev = []
+        self.calls = {}
+
+    def __enter__(self):
+        def timed(name, *a):
+            if name.endswith('_bytes') or name in ('ppp_pyset_order', 'ppp_pyset_pairs',
+                                                   'ppp_mws_host'):
+                return self.orig(name, *a)
+            e0 = self.torch.cuda.Event(enable_timing=True)
+            e1 = self.torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = self.orig(name, *a)
+            e1.record()
+            units = 0
+            if name in ('ppp_consensus', 'ppp_rank'):
+                units = int(a[5] if name == 'ppp_consensus' else a[4])
+            elif name in ('ppp_patch_graph', 'ppp_patch_graph_rows'):
+                units = int(a[5] if name == 'ppp_patch_graph' else a[6])
+            self.ev.append((name, e0, e1, units))
+            return r
+        self.cc.call = timed
+        return self
+
+    def __exit__(self, *exc):
+        self.cc.call = self.orig
+        self.torch.cuda.synchronize()
+        for name, e0, e1, units in self.ev:
+            d = self.calls.setdefault(name, dict(ms=0.0, calls=0, units=0))
+            d['ms'] += e0.elapsed_time(e1)
+            d['calls'] += 1
+            d['units'] += units
+        return False
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--shape', default=None, help='z,y,x (default: the FlyLight-sized volume)')
+    ap.add_argument('--chunk', default=None, help='z,y,x chunksize')
+    ap.add_argument('--workers', type=int, default=3)
+    ap.add_argument('--mws', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
 
     import torch
     import torch.distributed as dist
-    from patchperpix_b200 import cuda_code as cc, vote_instances as vi
+    from patchperpix_b200 import cuda_code as cc, sharded, synth, vote_instances as vi
+    from patchperpix_b200.assembly import RowSource
     from patchperpix_b200.layout import patch_geometry
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -255,28 +311,21 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     cc.init_cuda()
-
-    # count launches through the C ABI
-    launches = [0]
-    orig_call = cc.call
-
-    def counting_call(name, *a):
-        launches[0] += LAUNCHES.get(name, 0)
-        return orig_call(name, *a)
-    cc.call = counting_call
-    import patchperpix_b200.assembly as asm_mod
-    asm_mod.cc.call = counting_call
-
-    ps = np.array(WORKLOAD['patchshape'])
+    w = workload_from_args(args)
+    ps = np.array(w['patchshape'])
     _, P, _, _, _, K = patch_geometry(ps)
-    # every rank assembles its own copy of the SAME image: equal work per GPU (weak scaling)
-    pred, numinst, _ = make_inputs(dev, WORKLOAD['seed'])
-    mid = P // 2
-    fg = (pred[mid] > 0.5).to(torch.uint8)
-    overlap = torch.from_numpy((numinst > 1).astype(np.uint8)).to(dev)
-    mask = fg.clone()
-    mask[overlap > 0] = 0
-    nfg = int(fg.sum().item())
+    kw = dict(KW, patchshape=list(w['patchshape']), chunksize=list(w['chunksize']), mws=args.mws)
+    shape = w['shape']
+    axis, slabs = sharded.slab_partition(shape, w['chunksize'], world)
+    lo, hi = slabs[rank]
+
+    # ---- inputs: the patch rows of my slab, resident in HBM ---------------------
+    t_gen = time.perf_counter()
+    coords, patches, numinst = synth.neurite_rows(shape, ps, axis=axis, lo=lo, hi=hi,
+                                                  device=dev, **synth_kw(w))
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    n_own = int(coords.shape[0])
     steps, warm = args.steps, max(args.warmup, 3)
 
     def barrier():
@@ -284,142 +333,161 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing -------------------------------------------
+    def device_step():
+        shard = sharded.RowShard(shape, axis, lo, hi, coords, patches, numinst)
+        return sharded.stitch_shard(shard, slabs, workers=args.workers, **kw)
+
+    # ---- device-resident timing -------------------------------------------------
     for _ in range(warm):
-        device_step(pred, fg, overlap, mask, ps, KW)
+        inst, info = device_step()
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     barrier()
-    launches[0] = 0
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    F_rows = 0
-    for i in range(steps):
-        _, F_rows = device_step(pred, fg, overlap, mask, ps, KW, ev[i])
+    tw = time.perf_counter()
+    for _ in range(steps):
+        inst, info = device_step()
     t1.record()
     barrier()
-    n_launch = launches[0] // steps
+    wall_ms = (time.perf_counter() - tw) * 1e3 / steps
     ms = t0.elapsed_time(t1) / steps
-    cons_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    rank_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     clocks = sampler.summary()
 
-    # ---- end to end: pinned host inputs -> labels on the host -----------------
-    # the prediction as the predict step stores it: float16 [P,Z,Y,X]
-    # (predict_no_gp.py:243-257); to_instance_seg widens it on the device, which is
-    # the exact conversion loadAffinities does on the host (utilVoteInstances.py:136-250)
-    pred_h = torch.empty(pred.shape, dtype=torch.float16).pin_memory()
-    pred_h.copy_(pred)
-    assert torch.equal(pred_h.to(dev).float(), pred), "synthetic input is not f16-exact"
-    fg_h = fg.cpu().pin_memory()
-    numinst_h = torch.from_numpy(numinst).pin_memory()
-    h2d = pred_h.numel() * 2 + fg_h.numel() * 2 + numinst_h.numel()
-    d2h = fg_h.numel() * 2 + fg_h.numel()          # u16 labels + u8 foreground
-    # one sample after the other (what the reference's file loop does) ...
-    for _ in range(2):
-        vi.to_instance_seg(pred_h, fg_h, fg_h, numinst_h, ps, **KW)
+    # ---- end to end: pinned host rows -> uint16 labels of my slab on the host ------
+    coords_h = coords.cpu().pin_memory()
+    patches_h = patches.cpu().pin_memory()
+    numinst_h = numinst.cpu().pin_memory()
+    own_box = list(shape)
+    own_box[axis] = hi - lo
+    out_h = torch.empty(own_box, dtype=torch.int16).pin_memory()
+    h2d = coords_h.numel() * 4 + patches_h.numel() * 2 + numinst_h.numel()
+    d2h = out_h.numel() * 2
+
+    def e2e_step():
+        c = coords_h.to(dev, non_blocking=True)
+        p = patches_h.to(dev, non_blocking=True)
+        n = numinst_h.to(dev, non_blocking=True)
+        shard = sharded.RowShard(shape, axis, lo, hi, c, p, n)
+        inst_e, _ = sharded.stitch_shard(shard, slabs, workers=args.workers, **kw)
+        out_h.copy_(inst_e.to(torch.int16), non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_step()
     barrier()
     te = time.perf_counter()
     for _ in range(steps):
-        inst_e2e, _ = vi.to_instance_seg(pred_h, fg_h, fg_h, numinst_h, ps, **KW)
-    torch.cuda.synchronize()
-    e2e_serial_ms = (time.perf_counter() - te) * 1e3 / steps
-
-    # ... and through the multi-sample entry point, which uploads sample i+1 on a
-    # copy stream while sample i is assembled (every step still copies its own
-    # input from pinned memory inside the timed region and reads its labels back)
-    def feed(n):
-        for _ in range(n):
-            yield (pred_h, fg_h, fg_h, numinst_h)
-    for _ in vi.to_instance_seg_stream(feed(2), ps, **KW):
-        pass
+        e2e_step()
     barrier()
-    te = time.perf_counter()
-    for inst_s, _ in vi.to_instance_seg_stream(feed(steps), ps, **KW):
-        pass
-    torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - te) * 1e3 / steps
-    assert np.array_equal(inst_s, inst_e2e)
-    sys.stderr.write('[bench] rank %d: step %.2f ms  consensus %.2f  rank %.2f  e2e serial %.2f  '
-                     'e2e streamed %.2f ms\n' % (rank, ms, cons_ms, rank_ms, e2e_serial_ms, e2e_ms))
+    assert torch.equal(out_h.to(torch.int32), inst.cpu().to(torch.int16).to(torch.int32)), \
+        "end-to-end labels differ from the device-resident run"
 
-    # ---- max over ranks ------------------------------------------------------
-    tot_fg = nfg
+    # ---- per-call CUDA-event times: one extra single-stream pass --------------------
+    with CallTimer(cc, torch) as ct:
+        shard = sharded.RowShard(shape, axis, lo, hi, coords, patches, numinst)
+        sharded.stitch_shard(shard, slabs, workers=1, **kw)
+    calls = ct.calls
+    n_calls = sum(d['calls'] for d in calls.values())
+
+    # ---- digest of the whole label volume (equal for every N) ------------------------
+    full = sharded.gather_slabs(inst, slabs, axis, shape)
+    sha = None
+    n_inst = None
+    if rank == 0:
+        fh = full.to(torch.int16).cpu().numpy()
+        sha = hashlib.sha1(fh.tobytes()).hexdigest()[:16]
+        n_inst = int(info.get('n_labels', 0))
+    del full
+
+    sys.stderr.write('[bench] rank %d: rows %d  step %.1f ms (wall %.1f)  e2e %.1f ms  blocks %d '
+                     'faces %d  gen %.1f s\n' % (rank, n_own, ms, wall_ms, e2e_ms,
+                                                  info['my_blocks'], info['my_faces'], t_gen))
+    # ---- max over ranks ------------------------------------------------------------
+    tot_fg = n_own
+    halo = info['halo_bytes']
     if world > 1:
-        t = torch.tensor([ms, e2e_ms, cons_ms, rank_ms, e2e_serial_ms], device=dev,
-                         dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, cons_ms, rank_ms, e2e_serial_ms = (float(x) for x in t.tolist())
-        c = torch.tensor([nfg], device=dev, dtype=torch.int64)
+        ms, e2e_ms = (float(x) for x in t.tolist())
+        c = torch.tensor([n_own, halo, h2d, d2h], device=dev, dtype=torch.int64)
         dist.all_reduce(c)
-        tot_fg = int(c.item())
+        tot_fg, halo, h2d, d2h = (int(x) for x in c.tolist())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     peak, how = peaks()
-    # algorithmic bytes per fg voxel: consensus = own patch (f32) +
-    # 1 gate byte + K x (f32 affinity + integer counter); rank = patch + K consensus
-    # values + 1 score
-    b_unit = P * 4 + 1 + K * 8
-    achieved = b_unit * nfg / (cons_ms * 1e-3) / 1e9
-    b_rank = P * 4 + K * 4 + 4
-    # DRAM bytes per launch of the same kernels from the committed ncu capture
-    traffic = {}
-    tp = os.path.join(ROOT, 'profiles', 'r1_v9_traffic.json')
-    if os.path.exists(tp):
-        traffic = json.load(open(tp))
+    # algorithmic bytes per fg voxel, f16 input rows as consumed here:
+    # consensus = own patch (P x 2 B) + 1 gate byte + K x (f32 affinity + integer counter);
+    # rank = patch + K consensus values + 1 score
+    bytes_unit = dict(ppp_consensus=P * 2 + 1 + K * 8, ppp_rank=P * 2 + K * 4 + 4)
+    step_ms_profiled = sum(d['ms'] for d in calls.values())
+    roofs = []
+    for name in ('ppp_consensus', 'ppp_rank'):
+        d = calls.get(name)
+        if not d or d['ms'] <= 0:
+            continue
+        ach = bytes_unit[name] * d['units'] / (d['ms'] * 1e-3) / 1e9
+        roofs.append(dict(bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak,
+                          traffic=None, kernel=name, kernel_ms=d['ms'], launches=d['calls'],
+                          units=d['units'], bytes_per_fg_voxel=bytes_unit[name],
+                          share_of_gpu_time=d['ms'] / step_ms_profiled, peak_source=how,
+                          note='summed over the %d calls of one step (blocks + face regions); '
+                               'units = rows those calls processed' % d['calls']))
+    roofs.sort(key=lambda r: -r['kernel_ms'])
     line = dict(
         metric='consensus+assembly fg Mvoxels/s', value=tot_fg / (ms * 1e-3) / 1e6,
         unit='Mvoxels/s', n_gpus=world, steps=steps, warmup=warm, ms_per_step=ms,
-        higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+        higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32',
         data='synthetic',
-        config=dict(workload='configs[1]: 2D worms 696x520, patchshape 1x41x41, '
-                             '%d worms, one image per step per GPU' % WORKLOAD['n_worms'],
-                    fg_voxels_per_image=nfg, rows=F_rows,
-                    l2='inputs (2.4 GB prediction) larger than L2',
-                    flags='flylight [vote_instances] defaults, mws=False'),
+        config=dict(workload=workload_name(w), fg_voxels=tot_fg, slab_axis=axis,
+                    blocks=info['n_blocks'], faces=info['n_faces'], edges=info['n_edges'],
+                    instances=n_inst, labels_sha1=sha, block_workers=args.workers,
+                    halo_bytes_per_step=halo,
+                    l2='inputs (%.1f GB of patch rows) larger than L2' % (
+                        tot_fg * P * 2 / 1e9),
+                    flags='flylight [vote_instances] defaults, mws=%s' % args.mws),
         e2e=dict(value=tot_fg / (e2e_ms * 1e-3) / 1e6, unit='Mvoxels/s',
                  h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                 ms_per_step=e2e_ms, api='vote_instances.to_instance_seg_stream',
-                 serial_ms_per_step=e2e_serial_ms,
-                 input='float16 [P,Z,Y,X] pinned host buffer (the stored form), widened on the device'),
-        gpu_launches=n_launch, clocks=clocks,
+                 ms_per_step=e2e_ms, api='sharded.stitch_shard',
+                 input='pinned host rows: coords i32 [G,3], patches f16 [G,343], numinst u8 [G]',
+                 output='uint16 labels of the own slab, pinned host'),
+        gpu_launches=n_calls, clocks=clocks,
+        stage_ms={k: round(v['ms'], 3) for k, v in sorted(calls.items(), key=lambda kv: -kv[1]['ms'])},
     )
-    r_cons = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
-                  frac=achieved / peak, traffic=traffic.get('ppp_consensus'),
-                  kernel='ppp_consensus (consensus_count_kernel + consensus_rows_kernel)',
-                  kernel_ms=cons_ms, share_of_step=cons_ms / ms,
-                  bytes_per_fg_voxel=b_unit, peak_source=how,
-                  note='HBM is the bound SURVEY 8d assigns; the kernel itself is '
-                       'issue/latency-bound on ~1.8e10 pair visits (DESIGN.md section 6)')
-    a_rank = b_rank * nfg / (rank_ms * 1e-3) / 1e9
-    r_rank = dict(bound='hbm', achieved=a_rank, peak=peak, unit='GB/s', frac=a_rank / peak,
-                  traffic=traffic.get('ppp_rank'),
-                  kernel='ppp_rank (rank_lists_kernel + sort + rank_ref_kernel, reference '
-                         'summation order)',
-                  kernel_ms=rank_ms, share_of_step=rank_ms / ms, bytes_per_fg_voxel=b_rank,
-                  peak_source=how,
-                  note='serial float order fixed by the reference; 4-byte gathers from a '
-                       'consensus array larger than L2 (DESIGN.md section 6)')
-    first, second = (r_cons, r_rank) if cons_ms >= rank_ms else (r_rank, r_cons)
-    line['roofline'] = first
-    line['roofline_other'] = [second]
-    if not args.no_cpu_baseline:
+    if roofs:
+        line['roofline'] = roofs[0]
+        line['roofline_other'] = roofs[1:]
+    if not args.no_cpu_baseline and world == 1:
         try:
-            pn = pred.cpu().numpy()
-            Z, Y, X = CPU_SAMPLE
-            y0, x0 = (pn.shape[2] - Y) // 2, (pn.shape[3] - X) // 2
-            crop = np.ascontiguousarray(pn[:, :, y0:y0 + Y, x0:x0 + X])
-            ncrop = np.ascontiguousarray(numinst[:, y0:y0 + Y, x0:x0 + X])
-            n_c, dt = cpu_reference_step(crop, ncrop, tuple(int(p) for p in ps), KW)
+            cores = all_host_threads()
+            pred_s, ni_s, start = sample_region(w)
+            n_c, dt, inst_cpu = cpu_reference_step(pred_s, ni_s, tuple(int(p) for p in ps), KW)
+            # the same region through the CUDA path (rows form), labels must be identical
+            m = pred_s[P // 2] > np.float32(0.5)
+            c = np.argwhere(m)
+            v2r = torch.full(m.shape, -1, dtype=torch.int32)
+            v2r[c[:, 0], c[:, 1], c[:, 2]] = torch.arange(len(c), dtype=torch.int32)
+            rows = torch.from_numpy(np.ascontiguousarray(
+                pred_s[:, c[:, 0], c[:, 1], c[:, 2]].T.astype(np.float16)))
+            src = RowSource(rows.to(dev), v2r.to(dev))
+            fg_s = torch.from_numpy(m.astype(np.uint8)).to(dev)
+            inst_gpu, _ = vi.to_instance_seg(src, fg_s, fg_s.clone(), torch.from_numpy(ni_s).to(dev),
+                                             ps, **dict(KW, blockwise=False))
+            same = bool(np.array_equal(inst_gpu, inst_cpu))
+            line['parity_checked'] = same
             line['cpu_baseline'] = dict(
-                value=n_c / dt / 1e6, unit='Mvoxels/s', cores=os.cpu_count(),
-                kind='reference',
-                sample='centre crop %dx%d (%d fg voxels), all stages, %.1f s' % (Y, X, n_c, dt))
+                value=n_c / dt / 1e6, unit='Mvoxels/s', cores=cores, kind='reference',
+                sample='region %s at %s of the volume (%d fg voxels, %d instances), all stages, '
+                       'single block, %.1f s; GPU labels on the same region identical: %s' % (
+                           'x'.join(str(s) for s in m.shape), tuple(int(v) for v in start), n_c,
+                           int(inst_cpu.max()), dt, same))
+            if not same:
+                raise AssertionError('GPU labels differ from the CPU reference arm on the sample')
+        except AssertionError:
+            raise
         except Exception as e:          # the baseline must not take the bench down
             line['cpu_baseline'] = dict(value=None, unit='Mvoxels/s', cores=os.cpu_count(),
                                         kind='reference', sample='failed: %r' % (e,))

@@ -214,6 +214,34 @@ int ppp_paint_patches(const float* patches, const int32_t* nodes, int64_t m,
                       const int32_t* comp, const ppp_cfg* cfg, int32_t* instances,
                       void* stream);
 
+/* ---- compact patch rows: the form a ppp+dec run produces -------------------
+ * decode.py:39-65 decodes the foreground voxels only (everything else of the
+ * prediction volume stays zero) and stores float16 (decode.py:102-109).  Instead
+ * of scattering into a dense [P][Z][Y][X] array the patches stay ROWS:
+ *   patches  f16 [G][P]   (bit pattern as uint16_t; one row per stored voxel)
+ *   vox2row  i32 [V]      row of block voxel v in `patches`, or -1 = all-zero patch
+ * The *_rows entry points equal their dense counterparts on the dense array that
+ * scattering the rows would give (tests/test_rows_path.py). */
+int ppp_gate_rows(const uint16_t* patches, const int32_t* vox2row,
+                  const uint8_t* overlap, const uint8_t* cand,
+                  const ppp_cfg* cfg, uint8_t* flags, void* stream);
+int ppp_prepare_rows(const uint16_t* patches, const int32_t* vox2row,
+                     const uint8_t* flags, const int32_t* rowvox, int64_t F,
+                     const ppp_cfg* cfg, float* dp, uint32_t* fcmask,
+                     uint32_t* ptmask, uint64_t* rbits, void* stream);
+int ppp_patch_graph_rows(const uint16_t* patches, const int32_t* vox2row,
+                         const uint8_t* flags, const int32_t* fgidx,
+                         const float* cons, const uint32_t* pairs, int64_t n,
+                         const ppp_cfg* cfg, float* aff, void* scratch, void* stream);
+/* painting of graph nodes into a sub-volume `instances` i32 [cfg Z][Y][X] (zeroed
+ * by the caller): node i has its centre at node_zyx[i] (coordinates of that
+ * sub-volume; may lie outside, the window is clipped), its patch is row
+ * node_row[i], its component node_label[i] (<= 0: skipped); maximum wins
+ * (graph_to_labeling.py:84, "later components overwrite earlier ones"). */
+int ppp_paint_rows(const uint16_t* patches, const int32_t* node_row,
+                   const int32_t* node_zyx, const int32_t* node_label, int64_t m,
+                   const ppp_cfg* cfg, int32_t* instances, void* stream);
+
 /* ---- ppp+dec: code -> patch decoder on the tensor cores --------------------
  * (experiments/flylight/setups/setup01/decode.py:16-65 + Autoencoder.forward,
  * torch_model.py:523-544; flylight sizes: code 176 = 22 x 2^3, patch 7^3).

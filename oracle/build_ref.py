@@ -7,7 +7,8 @@ from . import ref_runner
 # (kind, dims, patchshape, th, flags, omp)
 BASE = ['-DUSE_LESS_THAN_TH', '-DOVERLAP']
 CONFIGS = []
-for dims, ps in (((1, 160, 160), (1, 41, 41)), ((1, 256, 256), (1, 41, 41)), ((24, 48, 48), (7, 7, 7))):
+for dims, ps in (((1, 160, 160), (1, 41, 41)), ((1, 256, 256), (1, 41, 41)), ((24, 48, 48), (7, 7, 7)),
+                 ((72, 72, 72), (7, 7, 7))):
     for omp in (False, True):
         CONFIGS += [
             ('fill', dims, ps, 0.5, BASE + ['-DNORM_PROB_PRODUCT'], omp),

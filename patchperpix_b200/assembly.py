@@ -101,10 +101,37 @@ def mutex_watershed(pairs, aff, cfg):
     return node_vox[:m].copy(), node_label[:m].copy(), int(top.value)
 
 
+class RowSource:
+    """compact prediction of one block (the form a ppp+dec run produces,
+    decode.py:39-65): `patches` f16 [G,P] cuda tensor, one row per stored voxel, and
+    `vox2row` i32 [Z,Y,X] cuda tensor = row of every block voxel or -1 (an all-zero
+    patch).  Stands in for the dense f32 [P,Z,Y,X] block everywhere."""
+
+    def __init__(self, patches, vox2row):
+        torch = _torch()
+        assert patches.dtype == torch.float16 and patches.is_contiguous()
+        assert vox2row.dtype == torch.int32 and vox2row.is_contiguous()
+        assert vox2row.dim() == 3
+        self.patches = patches
+        self.vox2row = vox2row
+        self.shape = tuple(int(s) for s in vox2row.shape)
+        self.device = patches.device
+
+    def dense(self):
+        """the equivalent f32 [P,Z,Y,X] tensor (tests only: this is what the rows
+        path avoids)."""
+        torch = _torch()
+        P = int(self.patches.shape[1])
+        out = torch.zeros((P,) + self.shape, dtype=torch.float32, device=self.device)
+        m = self.vox2row >= 0
+        out[:, m] = self.patches[self.vox2row[m].long()].float().T
+        return out
+
+
 class BlockAssembler:
     """state of one block on the device.
 
-    pred        f32 [P,Z,Y,X] cuda tensor (the block incl. its halo)
+    pred        f32 [P,Z,Y,X] cuda tensor (the block incl. its halo), or a RowSource
     foreground  host-side foreground (bool/u8 [Z,Y,X] cuda tensor): the
                 candidate patch centres (vote_instances.py:276-287)
     overlap     u8 [Z,Y,X] cuda tensor, numinst > 1 (vote_instances.py:211)
@@ -112,11 +139,18 @@ class BlockAssembler:
 
     def __init__(self, pred, foreground, overlap, patchshape, **kwargs):
         torch = _torch()
-        assert pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous()
-        self.pred = pred
-        self.shape = tuple(int(s) for s in pred.shape[1:])
         self.ps, self.P, self.rad, _, self.N, self.K = patch_geometry(patchshape)
-        assert pred.shape[0] == self.P, "channel count != prod(patchshape)"
+        if isinstance(pred, RowSource):
+            self.rows = pred
+            self.pred = None
+            self.shape = pred.shape
+            assert pred.patches.shape[1] == self.P, "row length != prod(patchshape)"
+        else:
+            assert pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous()
+            self.rows = None
+            self.pred = pred
+            self.shape = tuple(int(s) for s in pred.shape[1:])
+            assert pred.shape[0] == self.P, "channel count != prod(patchshape)"
         self.kwargs = kwargs
         self.cfg = cc.make_cfg(self.shape, self.ps, **kwargs)
         self.V = int(np.prod(self.shape))
@@ -135,8 +169,13 @@ class BlockAssembler:
         torch = _torch()
         V = self.V
         self.flags = torch.empty(V, dtype=torch.uint8, device=self.dev)
-        cc.call('ppp_gate', cc.ptr(self.pred), cc.ptr(self.overlap),
-                cc.ptr(self.foreground), self.cfg, cc.ptr(self.flags), self.stream)
+        if self.rows is not None:
+            cc.call('ppp_gate_rows', cc.ptr(self.rows.patches), cc.ptr(self.rows.vox2row),
+                    cc.ptr(self.overlap), cc.ptr(self.foreground), self.cfg,
+                    cc.ptr(self.flags), self.stream)
+        else:
+            cc.call('ppp_gate', cc.ptr(self.pred), cc.ptr(self.overlap),
+                    cc.ptr(self.foreground), self.cfg, cc.ptr(self.flags), self.stream)
         self.fgidx = torch.empty(V, dtype=torch.int32, device=self.dev)
         self.rowvox = torch.empty(V, dtype=torch.int32, device=self.dev)
         nrows = torch.zeros(1, dtype=torch.int64, device=self.dev)
@@ -156,9 +195,14 @@ class BlockAssembler:
         if want_dp and int(self.ps[2]) <= 64:
             self.rbits = torch.empty((int(self.ps[0] * self.ps[1]), F, 2), dtype=torch.int64,
                                      device=self.dev)
-        cc.call('ppp_prepare_patches', cc.ptr(self.pred), cc.ptr(self.flags),
-                cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.dp),
-                cc.ptr(self.fcmask), None, cc.ptr(self.rbits), self.stream)
+        if self.rows is not None:
+            cc.call('ppp_prepare_rows', cc.ptr(self.rows.patches), cc.ptr(self.rows.vox2row),
+                    cc.ptr(self.flags), cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.dp),
+                    cc.ptr(self.fcmask), None, cc.ptr(self.rbits), self.stream)
+        else:
+            cc.call('ppp_prepare_patches', cc.ptr(self.pred), cc.ptr(self.flags),
+                    cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.dp),
+                    cc.ptr(self.fcmask), None, cc.ptr(self.rbits), self.stream)
         self._prepared = True
         return self.F
 
@@ -307,9 +351,14 @@ class BlockAssembler:
             cfg = cc.make_cfg(self.shape, self.ps, **dict(self.kwargs, ppp_graph_fast=fast))
         scratch = torch.empty(cc.call('ppp_patch_graph_scratch_bytes', cfg, n),
                               dtype=torch.uint8, device=self.dev)
-        cc.call('ppp_patch_graph', cc.ptr(self.pred), cc.ptr(self.flags), cc.ptr(self.fgidx),
-                cc.ptr(self.cons), cc.ptr(pairs_dev), n, cfg, cc.ptr(aff), cc.ptr(scratch),
-                self.stream)
+        if self.rows is not None:
+            cc.call('ppp_patch_graph_rows', cc.ptr(self.rows.patches), cc.ptr(self.rows.vox2row),
+                    cc.ptr(self.flags), cc.ptr(self.fgidx), cc.ptr(self.cons), cc.ptr(pairs_dev),
+                    n, cfg, cc.ptr(aff), cc.ptr(scratch), self.stream)
+        else:
+            cc.call('ppp_patch_graph', cc.ptr(self.pred), cc.ptr(self.flags),
+                    cc.ptr(self.fgidx), cc.ptr(self.cons), cc.ptr(pairs_dev), n, cfg,
+                    cc.ptr(aff), cc.ptr(scratch), self.stream)
         return aff[:n]
 
     # -- step 6 ------------------------------------------------------------
@@ -342,6 +391,19 @@ class BlockAssembler:
 
     def _paint(self, pred, nodes, comp, cfg, n_comp, per_channel):
         torch = _torch()
+        if pred is None:                 # compact rows
+            if per_channel:
+                raise NotImplementedError("one_instance_per_channel needs the dense input form")
+            inst = torch.zeros(self.shape, dtype=torch.int32, device=self.dev)
+            nl = nodes.long()
+            Y, X = self.shape[1], self.shape[2]
+            zyx = torch.stack([nl // (Y * X), (nl // X) % Y, nl % X], dim=1).to(torch.int32)
+            node_row = self.rows.vox2row.reshape(-1)[nl].contiguous()
+            node_label = comp[nl].contiguous()
+            cc.call('ppp_paint_rows', cc.ptr(self.rows.patches), cc.ptr(node_row),
+                    cc.ptr(zyx.contiguous()), cc.ptr(node_label), int(nodes.numel()), cfg,
+                    cc.ptr(inst), self.stream)
+            return inst
         if per_channel:
             inst = torch.zeros((n_comp,) + self.shape, dtype=torch.int32, device=self.dev)
             if n_comp > 0:

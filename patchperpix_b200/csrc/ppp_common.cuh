@@ -1,6 +1,7 @@
 // Shared device helpers for the PatchPerPix B200 assembly kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include "../../include/ppp_b200.h"
 
@@ -40,6 +41,27 @@ __host__ __device__ inline Geo make_geo(const ppp_cfg& c)
     g.rp = c.psz * c.psy * g.rsg;
     return g;
 }
+
+// Where the patch predictions come from.  SrcDense = the reference's dense
+// float32 [P][Z][Y][X] block (vote_instances.py:193-200).  SrcRows = the compact
+// form a ppp+dec run produces (decode.py:39-65 decodes the foreground voxels only,
+// everything else stays zero): float16 [G][P] patch rows + vox2row[V] = row of
+// block voxel v in `patches`, or -1 (an all-zero patch).
+struct SrcDense {
+    const float* __restrict__ pred;
+    int64_t V;
+    __device__ __forceinline__ float at(int po, int64_t v) const { return pred[(int64_t)po * V + v]; }
+};
+struct SrcRows {
+    const __half* __restrict__ patches;
+    const int32_t* __restrict__ vox2row;
+    int P;
+    __device__ __forceinline__ float at(int po, int64_t v) const
+    {
+        const int r = vox2row[v];
+        return r < 0 ? 0.0f : __half2float(patches[(int64_t)r * P + po]);
+    }
+};
 
 __device__ __forceinline__ void vox_decode(const Geo& g, int v, int& z, int& y, int& x)
 {

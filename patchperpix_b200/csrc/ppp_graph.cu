@@ -32,7 +32,8 @@ __device__ __forceinline__ uint32_t pow_u32(uint32_t a, uint32_t e)
 // ordered compaction of the voting pixels of patch (cz,cy,cx) into smem
 // (computePatchGraph.cu:41-52): pred[mid][p] > TH and pred[po][c] > TH.
 // Also ranks the pixels that lie inside the other patch's window.
-__device__ int pg_build_list(const Geo& g, const ppp_cfg& cfg, const float* __restrict__ pred,
+template <class Src>
+__device__ int pg_build_list(const Geo& g, const ppp_cfg& cfg, const Src& pred,
                              const uint8_t* __restrict__ flags, int cz, int cy, int cx,
                              int oz, int oy, int ox,       // the other centre
                              int16_t* s_po, int16_t* s_ii, int* s_scratch, int* n_inter)
@@ -51,7 +52,7 @@ __device__ int pg_build_list(const Geo& g, const ppp_cfg& cfg, const float* __re
             int z = cz + qz - g.rz, y = cy + qy - g.ry, x = cx + qx - g.rx;
             if (z >= 0 && z < g.Z && y >= 0 && y < g.Y && x >= 0 && x < g.X) {
                 int pv = (z * g.Y + y) * g.X + x;
-                vote = (flags[pv] & PPP_FLAG_FG) && pred[(int64_t)po * g.V + vc] > cfg.th_gt;
+                vote = (flags[pv] & PPP_FLAG_FG) && pred.at(po, vc) > cfg.th_gt;
                 inter = vote && abs(x - ox) <= g.rx && abs(y - oy) <= g.ry && abs(z - oz) <= g.rz;
             }
         }
@@ -79,8 +80,9 @@ __device__ int pg_build_list(const Geo& g, const ppp_cfg& cfg, const float* __re
     return s_scratch[16];
 }
 
+template <class Src>
 __global__ void __launch_bounds__(PG_THREADS)
-patch_graph_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags,
+patch_graph_kernel(Src pred, const uint8_t* __restrict__ flags,
                    const int32_t* __restrict__ fgidx, const float* __restrict__ cons,
                    const uint32_t* __restrict__ pairs, ppp_cfg cfg, float* __restrict__ aff)
 {
@@ -178,7 +180,8 @@ patch_graph_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ f
 // ordered compaction of the voting pixels of patch (cz,cy,cx) (computePatchGraph.cu:41-52):
 // s_q = coordinates relative to (rz0,ry0,rx0), biased, packed z<<20|y<<10|x; s_row =
 // consensus row of the pixel; s_ii = rank among the pixels inside the other window, or -1
-__device__ int pgr_build_list(const Geo& g, const ppp_cfg& cfg, const float* __restrict__ pred,
+template <class Src>
+__device__ int pgr_build_list(const Geo& g, const ppp_cfg& cfg, const Src& pred,
                               const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
                               int cz, int cy, int cx, int oz, int oy, int ox,
                               int rz0, int ry0, int rx0,
@@ -199,7 +202,7 @@ __device__ int pgr_build_list(const Geo& g, const ppp_cfg& cfg, const float* __r
             int z = cz + qz - g.rz, y = cy + qy - g.ry, x = cx + qx - g.rx;
             if (z >= 0 && z < g.Z && y >= 0 && y < g.Y && x >= 0 && x < g.X) {
                 int pv = (z * g.Y + y) * g.X + x;
-                vote = (flags[pv] & PPP_FLAG_FG) && pred[(int64_t)po * g.V + vc] > cfg.th_gt;
+                vote = (flags[pv] & PPP_FLAG_FG) && pred.at(po, vc) > cfg.th_gt;
                 inter = vote && abs(x - ox) <= g.rx && abs(y - oy) <= g.ry && abs(z - oz) <= g.rz;
                 if (vote) {
                     row = fgidx[pv];
@@ -235,9 +238,9 @@ __device__ int pgr_build_list(const Geo& g, const ppp_cfg& cfg, const float* __r
 
 // LCG = false: every pair has a zero coordinate product (2-D data, z = 0): the sub-sampling
 // state stays 0 and nothing is ever skipped, so the factor tables are not needed
-template <bool LCG>
+template <bool LCG, class Src>
 __global__ void __launch_bounds__(PGR_THREADS)
-patch_graph_ref_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags,
+patch_graph_ref_kernel(Src pred, const uint8_t* __restrict__ flags,
                        const int32_t* __restrict__ fgidx, const float* __restrict__ cons,
                        const uint32_t* __restrict__ pairs, ppp_cfg cfg, float* __restrict__ aff,
                        int32_t* __restrict__ lists)
@@ -387,10 +390,10 @@ extern "C" int64_t ppp_patch_graph_scratch_bytes(const ppp_cfg* cfg, int64_t n)
     return (n > 0 ? n : 0) * (int64_t)g.P * 24 + 256;     // two pixel lists per pair
 }
 
-extern "C" int ppp_patch_graph(const float* pred, const uint8_t* flags,
-                               const int32_t* fgidx, const float* cons,
-                               const uint32_t* pairs, int64_t n, const ppp_cfg* cfg,
-                               float* aff, void* scratch, void* stream)
+template <class Src>
+static int patch_graph_launch(Src src, const uint8_t* flags, const int32_t* fgidx,
+                              const float* cons, const uint32_t* pairs, int64_t n,
+                              const ppp_cfg* cfg, float* aff, void* scratch, void* stream)
 {
     if (n <= 0) return 0;
     Geo g = make_geo(*cfg);
@@ -403,23 +406,43 @@ extern "C" int ppp_patch_graph(const float* pred, const uint8_t* flags,
         const bool lcg = g.Z > 1;
         if (scratch == nullptr) return ppp_fail(-1, "ppp_patch_graph: scratch required");
         if (lcg)
-            patch_graph_ref_kernel<true><<<(unsigned)n, PGR_THREADS, 0, (cudaStream_t)stream>>>(
-                pred, flags, fgidx, cons, pairs, *cfg, aff, (int32_t*)scratch);
+            patch_graph_ref_kernel<true, Src><<<(unsigned)n, PGR_THREADS, 0, (cudaStream_t)stream>>>(
+                src, flags, fgidx, cons, pairs, *cfg, aff, (int32_t*)scratch);
         else
-            patch_graph_ref_kernel<false><<<(unsigned)n, PGR_THREADS, 0, (cudaStream_t)stream>>>(
-                pred, flags, fgidx, cons, pairs, *cfg, aff, (int32_t*)scratch);
+            patch_graph_ref_kernel<false, Src><<<(unsigned)n, PGR_THREADS, 0, (cudaStream_t)stream>>>(
+                src, flags, fgidx, cons, pairs, *cfg, aff, (int32_t*)scratch);
         return ppp_check("ppp_patch_graph(reference order)");
     }
     size_t smem = (size_t)g.P * 12 + 16;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(patch_graph_kernel,
+        cudaError_t e = cudaFuncSetAttribute(patch_graph_kernel<Src>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return ppp_fail((int)e, "ppp_patch_graph: smem attribute");
     }
-    patch_graph_kernel<<<(unsigned)n, PG_THREADS, smem, (cudaStream_t)stream>>>(
-        pred, flags, fgidx, cons, pairs, *cfg, aff);
+    patch_graph_kernel<Src><<<(unsigned)n, PG_THREADS, smem, (cudaStream_t)stream>>>(
+        src, flags, fgidx, cons, pairs, *cfg, aff);
     return ppp_check("ppp_patch_graph");
+}
+
+extern "C" int ppp_patch_graph(const float* pred, const uint8_t* flags,
+                               const int32_t* fgidx, const float* cons,
+                               const uint32_t* pairs, int64_t n, const ppp_cfg* cfg,
+                               float* aff, void* scratch, void* stream)
+{
+    Geo g = make_geo(*cfg);
+    return patch_graph_launch(SrcDense{pred, g.V}, flags, fgidx, cons, pairs, n, cfg, aff,
+                              scratch, stream);
+}
+
+extern "C" int ppp_patch_graph_rows(const uint16_t* patches, const int32_t* vox2row,
+                                    const uint8_t* flags, const int32_t* fgidx,
+                                    const float* cons, const uint32_t* pairs, int64_t n,
+                                    const ppp_cfg* cfg, float* aff, void* scratch, void* stream)
+{
+    Geo g = make_geo(*cfg);
+    return patch_graph_launch(SrcRows{(const __half*)patches, vox2row, g.P}, flags, fgidx, cons,
+                              pairs, n, cfg, aff, scratch, stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -704,4 +727,42 @@ extern "C" int ppp_paint_patches(const float* patches, const int32_t* nodes, int
     paint_patches_kernel<<<(unsigned)m, 128, 0, (cudaStream_t)stream>>>(patches, nodes, comp,
                                                                          *cfg, instances);
     return ppp_check("ppp_paint_patches");
+}
+
+// ---------------------------------------------------------------------------
+// painting from float16 patch ROWS into a sub-volume (sharded blockwise path):
+// node i sits at (cz,cy,cx) in the coordinates of `instances` (shape cfg Z,Y,X;
+// the centre itself may lie outside, its window is clipped), its patch is row
+// node_row[i] of `patches`, its component node_label[i] (<= 0: not painted).
+// ---------------------------------------------------------------------------
+__global__ void paint_rows_kernel(const __half* __restrict__ patches,
+                                  const int32_t* __restrict__ node_row,
+                                  const int32_t* __restrict__ node_zyx,
+                                  const int32_t* __restrict__ node_label, ppp_cfg cfg,
+                                  int32_t* __restrict__ instances)
+{
+    Geo g = make_geo(cfg);
+    const int64_t i = blockIdx.x;
+    const int c = node_label[i];
+    const int r = node_row[i];
+    if (c <= 0 || r < 0) return;
+    const int cz = node_zyx[3 * i], cy = node_zyx[3 * i + 1], cx = node_zyx[3 * i + 2];
+    for (int po = threadIdx.x; po < g.P; po += blockDim.x) {
+        int qz, qy, qx;
+        po_decode(g, po, qz, qy, qx);
+        int z = cz + qz - g.rz, y = cy + qy - g.ry, x = cx + qx - g.rx;
+        if (z < 0 || z >= g.Z || y < 0 || y >= g.Y || x < 0 || x >= g.X) continue;
+        if (__half2float(patches[(int64_t)r * g.P + po]) > cfg.pt_gt)
+            atomicMax(&instances[((int64_t)z * g.Y + y) * g.X + x], c);
+    }
+}
+
+extern "C" int ppp_paint_rows(const uint16_t* patches, const int32_t* node_row,
+                              const int32_t* node_zyx, const int32_t* node_label, int64_t m,
+                              const ppp_cfg* cfg, int32_t* instances, void* stream)
+{
+    if (m <= 0) return 0;
+    paint_rows_kernel<<<(unsigned)m, 128, 0, (cudaStream_t)stream>>>(
+        (const __half*)patches, node_row, node_zyx, node_label, *cfg, instances);
+    return ppp_check("ppp_paint_rows");
 }

@@ -8,7 +8,8 @@
 // ---------------------------------------------------------------------------
 // gate: flags[v] = FG | GATED | CENTRE  (fillConsensusArray.cu:25-33, 53-60)
 // ---------------------------------------------------------------------------
-__global__ void gate_kernel(const float* __restrict__ pred_mid,
+template <class Src>
+__global__ void gate_kernel(Src src, int mid,
                             const uint8_t* __restrict__ overlap,
                             const uint8_t* __restrict__ cand,
                             ppp_cfg cfg, uint8_t* __restrict__ flags)
@@ -18,7 +19,7 @@ __global__ void gate_kernel(const float* __restrict__ pred_mid,
     if (v >= g.V) return;
     int z, y, x;
     vox_decode(g, (int)v, z, y, x);
-    bool fg = pred_mid[v] > cfg.th_gt;
+    bool fg = src.at(mid, v) > cfg.th_gt;
     bool ov = cfg.use_overlap && overlap != nullptr && overlap[v] != 0;
     bool interior = x >= g.rx && x < g.X - g.rx && y >= g.ry && y < g.Y - g.ry &&
                     z >= g.rz && z < g.Z - g.rz;
@@ -40,9 +41,22 @@ extern "C" int ppp_gate(const float* pred, const uint8_t* overlap, const uint8_t
     int mid = g.P / 2;
     int threads = 256;
     int64_t blocks = (g.V + threads - 1) / threads;
-    gate_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        pred + (int64_t)mid * g.V, overlap, cand, *cfg, flags);
+    gate_kernel<SrcDense><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        SrcDense{pred, g.V}, mid, overlap, cand, *cfg, flags);
     return ppp_check("ppp_gate");
+}
+
+extern "C" int ppp_gate_rows(const uint16_t* patches, const int32_t* vox2row,
+                             const uint8_t* overlap, const uint8_t* cand,
+                             const ppp_cfg* cfg, uint8_t* flags, void* stream)
+{
+    Geo g = make_geo(*cfg);
+    if (g.V <= 0 || g.V > 0x7fffffffLL) return ppp_fail(-1, "ppp_gate_rows: bad volume size");
+    int threads = 256;
+    int64_t blocks = (g.V + threads - 1) / threads;
+    gate_kernel<SrcRows><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        SrcRows{(const __half*)patches, vox2row, g.P}, g.P / 2, overlap, cand, *cfg, flags);
+    return ppp_check("ppp_gate_rows");
 }
 
 // ---------------------------------------------------------------------------
@@ -243,8 +257,9 @@ prepare_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags
 // rbits u64 [psz*psy][F][2] (line major: the consensus kernels read one word pair
 // per centre line from CONSECUTIVE partner rows, which are then contiguous).
 // ---------------------------------------------------------------------------
+template <class Src>
 __global__ void __launch_bounds__(128)
-received_bits_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ flags,
+received_bits_kernel(Src src, const uint8_t* __restrict__ flags,
                      const int32_t* __restrict__ rowvox, int64_t F, ppp_cfg cfg,
                      unsigned long long* __restrict__ rbits)
 {
@@ -267,7 +282,7 @@ received_bits_kernel(const float* __restrict__ pred, const uint8_t* __restrict__
                 if (cx < g.rx || cx >= g.X - g.rx) continue;
                 if (!(flags[line + cx] & PPP_FLAG_CENTRE)) continue;
                 // pixel b seen from centre c sits at patch index r - d
-                float val = pred[(int64_t)(porow + (g.psx - 1 - t)) * g.V + line + cx];
+                float val = src.at(porow + (g.psx - 1 - t), line + cx);
                 if (val > cfg.th_gt) hb |= 1ull << t;
                 else if (val < cfg.bg_lt) lb |= 1ull << t;
             }
@@ -292,8 +307,77 @@ extern "C" int ppp_prepare_patches(const float* pred, const uint8_t* flags,
     if (rbits != nullptr) {
         if (g.psx > 64) return ppp_fail(-1, "ppp_prepare_patches: psx > 64 has no bit path");
         dim3 grid2((unsigned)((F + 127) / 128), (unsigned)(g.psz * g.psy));
-        received_bits_kernel<<<grid2, 128, 0, (cudaStream_t)stream>>>(
-            pred, flags, rowvox, F, *cfg, (unsigned long long*)rbits);
+        received_bits_kernel<SrcDense><<<grid2, 128, 0, (cudaStream_t)stream>>>(
+            SrcDense{pred, g.V}, flags, rowvox, F, *cfg, (unsigned long long*)rbits);
     }
     return ppp_check("ppp_prepare_patches");
+}
+
+// ---------------------------------------------------------------------------
+// the same from float16 patch ROWS (compact ppp+dec form): one warp per row,
+// lanes walk the patch, so the source reads (consecutive po of one row) and the
+// dp / mask writes are coalesced without a transpose tile.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prepare_rows_kernel(const __half* __restrict__ patches, const int32_t* __restrict__ vox2row,
+                    const uint8_t* __restrict__ flags, const int32_t* __restrict__ rowvox,
+                    int64_t F, ppp_cfg cfg, float* __restrict__ dp,
+                    uint32_t* __restrict__ fcmask, uint32_t* __restrict__ ptmask)
+{
+    Geo g = make_geo(cfg);
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= F) return;
+    const int v = rowvox[row];
+    int z, y, x;
+    vox_decode(g, v, z, y, x);
+    const uint8_t fl = flags[v];
+    const bool centre = (fl & PPP_FLAG_CENTRE) != 0, interior = (fl & PPP_FLAG_INTERIOR) != 0;
+    const int srow = vox2row[v];
+    const __half* prow = patches + (int64_t)(srow < 0 ? 0 : srow) * g.P;
+    for (int base = 0; base < g.W * 32; base += 32) {
+        const int po = base + lane;
+        float d = 0.0f;
+        bool b1 = false, b2 = false;
+        if (interior && srow >= 0 && po < g.P) {
+            const float val = __half2float(prow[po]);
+            if (centre) {
+                int qz, qy, qx;
+                po_decode(g, po, qz, qy, qx);
+                int pv = ((z + qz - g.rz) * g.Y + (y + qy - g.ry)) * g.X + (x + qx - g.rx);
+                if (flags[pv] & PPP_FLAG_GATED) d = fold_class(val, cfg.th_gt, cfg.bg_lt);
+            }
+            b1 = val > cfg.fc_gt;
+            b2 = val > cfg.pt_gt;
+        }
+        if (dp != nullptr && po < g.P) dp[dp_index(g, F, row, po)] = d;
+        unsigned m1 = __ballot_sync(0xffffffffu, b1);
+        unsigned m2 = __ballot_sync(0xffffffffu, b2);
+        if (lane == 0) {
+            if (fcmask != nullptr) fcmask[row * g.W + (base >> 5)] = m1;
+            if (ptmask != nullptr) ptmask[row * g.W + (base >> 5)] = m2;
+        }
+    }
+    if (dp != nullptr)
+        for (int pr = lane; pr < g.psz * g.psy; pr += 32)
+            dp[((int64_t)pr * F + row) * g.rsg] = __int_as_float(x);
+}
+
+extern "C" int ppp_prepare_rows(const uint16_t* patches, const int32_t* vox2row,
+                                const uint8_t* flags, const int32_t* rowvox, int64_t F,
+                                const ppp_cfg* cfg, float* dp, uint32_t* fcmask,
+                                uint32_t* ptmask, uint64_t* rbits, void* stream)
+{
+    if (F <= 0) return 0;
+    Geo g = make_geo(*cfg);
+    prepare_rows_kernel<<<(unsigned)((F + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)patches, vox2row, flags, rowvox, F, *cfg, dp, fcmask, ptmask);
+    if (rbits != nullptr) {
+        if (g.psx > 64) return ppp_fail(-1, "ppp_prepare_rows: psx > 64 has no bit path");
+        dim3 grid2((unsigned)((F + 127) / 128), (unsigned)(g.psz * g.psy));
+        received_bits_kernel<SrcRows><<<grid2, 128, 0, (cudaStream_t)stream>>>(
+            SrcRows{(const __half*)patches, vox2row, g.P}, flags, rowvox, F, *cfg,
+            (unsigned long long*)rbits);
+    }
+    return ppp_check("ppp_prepare_rows");
 }

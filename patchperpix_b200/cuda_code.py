@@ -128,6 +128,10 @@ _SIGS = {
     'ppp_paint': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
     'ppp_paint_channels': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
     'ppp_paint_patches': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
+    'ppp_gate_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'cfg', 'p', 'p']),
+    'ppp_prepare_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p', 'p', 'p']),
+    'ppp_patch_graph_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
+    'ppp_paint_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p']),
     'ppp_decode_scratch_bytes': (ctypes.c_int64, ['i64']),
     'ppp_decode': (ctypes.c_int, ['p', 'i64'] + ['p'] * 14 + ['i32', 'p', 'p', 'p']),
 }

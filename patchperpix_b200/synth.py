@@ -41,17 +41,21 @@ def _hash01_torch(idx, seed):
 # ----------------------------------------------------------------------------
 # label volumes
 # ----------------------------------------------------------------------------
-def _draw_capsule(labels, numinst, p0, p1, radius, value):
-    """paint all voxels within `radius` of segment p0-p1 (float zyx coords)."""
+def _draw_capsule(labels, numinst, p0, p1, radius, value, origin=None):
+    """paint all voxels within `radius` of segment p0-p1 (float zyx coords).
+    `origin`: global coordinates of labels[0,0,0] (labels is a window of the volume)."""
     shape = labels.shape
+    org = np.zeros(3, int) if origin is None else np.asarray(origin, int)
     lo = np.floor(np.minimum(p0, p1) - radius).astype(int)
     hi = np.ceil(np.maximum(p0, p1) + radius).astype(int) + 1
-    lo = np.maximum(lo, 0)
-    hi = np.minimum(hi, shape)
+    lo = np.maximum(lo, org)
+    hi = np.minimum(hi, org + np.asarray(shape))
     if np.any(hi <= lo):
         return None
     zz, yy, xx = np.meshgrid(*[np.arange(lo[i], hi[i]) for i in range(3)],
                              indexing='ij')
+    lo = lo - org
+    hi = hi - org
     pts = np.stack([zz, yy, xx], axis=-1).astype(np.float32)
     d = (p1 - p0).astype(np.float32)
     dd = float(np.dot(d, d))
@@ -65,11 +69,11 @@ def _draw_capsule(labels, numinst, p0, p1, radius, value):
     return (slice(lo[0], hi[0]), slice(lo[1], hi[1]), slice(lo[2], hi[2])), m
 
 
-def _paint_polyline(labels, numinst, pts, radius, value):
+def _paint_polyline(labels, numinst, pts, radius, value, origin=None):
     """union of capsules = one instance (counts once per voxel in numinst)."""
     for a, b in zip(pts[:-1], pts[1:]):
         res = _draw_capsule(labels, numinst, np.asarray(a, np.float32),
-                            np.asarray(b, np.float32), radius, value)
+                            np.asarray(b, np.float32), radius, value, origin)
         if res is None:
             continue
         sl, m = res
@@ -129,12 +133,23 @@ def blobs_3d(shape=(128, 512, 512), n=2500, seed=3,
 
 
 def neurites_3d(shape=(256, 1024, 1024), n=300, seed=4, radius=(2, 3),
-                seg_len=24.0, n_seg=40):
-    """FlyLight-style thin 3-D polylines."""
+                seg_len=24.0, n_seg=40, window=None):
+    """FlyLight-style thin 3-D polylines.
+    window = (axis, lo, hi): only that slab of the volume is allocated and drawn
+    (same random sequence, so the slabs of different ranks fit together)."""
     rng = np.random.default_rng(seed)
     shape = tuple(int(s) for s in shape)
-    labels = np.zeros(shape, np.int32)
-    numinst = np.zeros(shape, np.uint8)
+    origin = None
+    wshape = shape
+    if window is not None:
+        ax, wlo, whi = window
+        origin = np.zeros(3, int)
+        origin[ax] = wlo
+        wshape = list(shape)
+        wshape[ax] = whi - wlo
+        wshape = tuple(wshape)
+    labels = np.zeros(wshape, np.int32)
+    numinst = np.zeros(wshape, np.uint8)
     for i in range(n):
         p = np.array([rng.uniform(0, shape[0]), rng.uniform(0, shape[1]),
                       rng.uniform(0, shape[2])])
@@ -151,8 +166,70 @@ def neurites_3d(shape=(256, 1024, 1024), n=300, seed=4, radius=(2, 3),
             pts.append(p.copy())
             if np.any(p < -seg_len) or np.any(p > np.array(shape) + seg_len):
                 break
-        _paint_polyline(labels, numinst, pts, r, i + 1)
+        _paint_polyline(labels, numinst, pts, r, i + 1, origin)
     return labels, numinst
+
+
+def neurite_rows(shape, patchshape, axis=0, lo=0, hi=None, seed=4, noise=0.04, device='cuda',
+                 chunk_rows=1 << 17, box=None, **kw):
+    """the compact row form of make_case('neurites', ...) for the slab
+    lo <= coord[axis] < hi: (coords i32 [G,3] global, patches f16 [G,P], numinst u8 [G])
+    as torch tensors on `device`, rows in raster order.  Values are bit-identical to
+    patches_from_labels on the whole volume at the stored voxels (labels > 0); every
+    other voxel of a ppp+dec prediction is zero (decode.py:39-65)."""
+    import torch
+    ps = [int(p) for p in patchshape]
+    r = [p // 2 for p in ps]
+    shape = tuple(int(s) for s in shape)
+    hi = shape[axis] if hi is None else hi
+    wlo, whi = max(lo - r[axis], 0), min(hi + r[axis], shape[axis])
+    labels, numinst = neurites_3d(shape, seed=seed, window=(axis, wlo, whi), **kw)
+    dev = torch.device(device)
+    lab_t = torch.as_tensor(labels, device=dev)
+    ni_t = torch.as_tensor(numinst, device=dev)
+    # -1 outside the VOLUME; inside the window margin the real labels are present
+    pad = [r[2], r[2], r[1], r[1], r[0], r[0]]
+    pad_lo = [r[0], r[1], r[2]]
+    pad[2 * (2 - axis)] = r[axis] - (lo - wlo)           # window margin already there
+    pad[2 * (2 - axis) + 1] = r[axis] - (whi - hi)
+    pad_lo[axis] = r[axis] - (lo - wlo)
+    lab = torch.nn.functional.pad(lab_t, pad, value=-1)
+    own = [slice(None)] * 3
+    own[axis] = slice(lo - wlo, hi - wlo)
+    c = torch.nonzero(lab_t[tuple(own)] > 0)             # raster order, slab-local
+    if box is not None:                                  # only the rows inside a 3-D box
+        b0 = torch.as_tensor(np.asarray(box[0]), device=dev).clone()
+        b1 = torch.as_tensor(np.asarray(box[1]), device=dev).clone()
+        b0[axis] -= lo
+        b1[axis] -= lo
+        c = c[((c >= b0) & (c < b1)).all(dim=1)]
+    G = int(c.shape[0])
+    P = ps[0] * ps[1] * ps[2]
+    V = shape[0] * shape[1] * shape[2]
+    gc = c.clone()
+    gc[:, axis] += lo
+    vglob = (gc[:, 0] * shape[1] + gc[:, 1]) * shape[2] + gc[:, 2]
+    wc = c.clone()
+    wc[:, axis] += lo - wlo
+    lab_c = lab_t[wc[:, 0], wc[:, 1], wc[:, 2]]
+    ni_c = ni_t[wc[:, 0], wc[:, 1], wc[:, 2]]
+    offs = torch.tensor([(dz, dy, dx) for dz in range(ps[0]) for dy in range(ps[1])
+                         for dx in range(ps[2])], device=dev)          # [P,3], padded coords
+    po = torch.arange(P, device=dev, dtype=torch.int64)
+    patches = torch.empty((G, P), dtype=torch.float16, device=dev)
+    # position of centre c in the padded window: wc + pad_lo - r  (offset adds 0..ps-1)
+    basec = wc + torch.tensor([pad_lo[i] - r[i] for i in range(3)], device=dev)
+    for s0 in range(0, G, chunk_rows):
+        s1 = min(s0 + chunk_rows, G)
+        q = basec[s0:s1, None, :] + offs[None, :, :]
+        nb = lab[q[..., 0], q[..., 1], q[..., 2]]
+        ideal = (nb == lab_c[s0:s1, None]).to(torch.float32)
+        idx = po[None, :] * V + vglob[s0:s1, None]
+        u = _hash01_torch(idx, seed)
+        v = ideal * 0.9 + 0.05
+        v = v + (u * 2.0 - 1.0) * noise
+        patches[s0:s1] = v.to(torch.float16)
+    return gc.to(torch.int32), patches, ni_c.to(torch.uint8)
 
 
 def discs_2d(shape_yx=(48, 48), centers=((16, 16), (30, 32)), radius=8):

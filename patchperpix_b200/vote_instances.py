@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 from . import cuda_code
-from .assembly import BlockAssembler
+from .assembly import BlockAssembler, RowSource
 from .utilVoteInstances import loadAffinities, getResKey
 
 logger = logging.getLogger(__name__)
@@ -97,8 +97,11 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
     rad = np.array([p // 2 for p in patchshape])
     ret_inter = kwargs.get('return_intermediates', False)
 
-    fg_np_in = foreground
-    pred = _to_device(pred_affs, torch.float32)
+    if isinstance(pred_affs, RowSource):       # compact rows (ppp+dec form), device resident
+        pred = pred_affs
+        assert not kwargs.get("pad_with_ps", False), "pad_with_ps needs the dense input form"
+    else:
+        pred = _to_device(pred_affs, torch.float32)
     fg = _to_device(foreground, torch.uint8)
     mask = _to_device(mask_to_cover, torch.uint8).clone()
     numinst_t = _to_device(numinst)
