@@ -401,8 +401,9 @@ def main():
     del full
 
     sys.stderr.write('[bench] rank %d: rows %d  step %.1f ms (wall %.1f)  e2e %.1f ms  blocks %d '
-                     'faces %d  gen %.1f s\n' % (rank, n_own, ms, wall_ms, e2e_ms,
-                                                  info['my_blocks'], info['my_faces'], t_gen))
+                     'faces %d  gen %.1f s  phases %s\n' % (
+                         rank, n_own, ms, wall_ms, e2e_ms, info['my_blocks'], info['my_faces'],
+                         t_gen, {k: round(v, 1) for k, v in info['phase_ms'].items()}))
     # ---- max over ranks ------------------------------------------------------------
     tot_fg = n_own
     halo = info['halo_bytes']
@@ -455,6 +456,7 @@ def main():
                  input='pinned host rows: coords i32 [G,3], patches f16 [G,343], numinst u8 [G]',
                  output='uint16 labels of the own slab, pinned host'),
         gpu_launches=n_calls, clocks=clocks,
+        phase_ms={k: round(v, 2) for k, v in info['phase_ms'].items()},
         stage_ms={k: round(v['ms'], 3) for k, v in sorted(calls.items(), key=lambda kv: -kv[1]['ms'])},
     )
     if roofs:

@@ -114,6 +114,26 @@ int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8_t* flags,
                   const ppp_cfg* cfg, float* cons, uint32_t* cnt, int32_t impl,
                   void* scratch, void* stream);
 
+/* small windows (psx <= 8, psz*psy <= 64: the 7^3 flylight patches): "received"
+ * tables, one contiguous row per voxel instead of gathers into the centre-major
+ * array.  rv f32 [F][P]: rv[row(b)][d] = class-folded value the centre b + d
+ * (d in window raster order) assigns to b, 0 if that voxel is no patch centre or
+ * b is not gated; rb16 u16 [F][W16], W16 = ppp_received_row_words(cfg): word
+ * (dz,dy) = (background bits << 8) | high bits of the same table.
+ * ppp_consensus_small gives bit-identical cons / cnt to ppp_consensus (same
+ * centre order).  need u8 [F] or NULL: rows with 0 are skipped and left
+ * unwritten (callers that only read the rows of known patches). */
+int32_t ppp_received_row_words(const ppp_cfg* cfg);
+int ppp_received(const float* pred, const uint8_t* flags, const int32_t* rowvox,
+                 int64_t F, const ppp_cfg* cfg, float* rv, uint16_t* rb16, void* stream);
+int ppp_received_rows(const uint16_t* patches, const int32_t* vox2row,
+                      const uint8_t* flags, const int32_t* rowvox, int64_t F,
+                      const ppp_cfg* cfg, float* rv, uint16_t* rb16, void* stream);
+int ppp_consensus_small(const float* rv, const uint16_t* rb16, const uint8_t* flags,
+                        const int32_t* fgidx, const int32_t* rowvox,
+                        const uint8_t* need, int64_t F, const ppp_cfg* cfg,
+                        float* cons, uint32_t* cnt, void* stream);
+
 /* ---- step 2: rank (rankPatches.cu) ----------------------------------------
  * score f32 [Z][Y][X]: border voxels -1 / -9999999, non-fg interior 0. */
 int64_t ppp_rank_scratch_bytes(const ppp_cfg* cfg, int64_t F);

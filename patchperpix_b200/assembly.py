@@ -165,7 +165,7 @@ class BlockAssembler:
         self._prepared = False
 
     # -- step 0 ------------------------------------------------------------
-    def prepare(self, want_dp=True):
+    def prepare(self, want_dp=True, want_rbits=None):
         torch = _torch()
         V = self.V
         self.flags = torch.empty(V, dtype=torch.uint8, device=self.dev)
@@ -192,7 +192,17 @@ class BlockAssembler:
                               device=self.dev) if want_dp else None
         self.fcmask = torch.empty((F, self.W), dtype=torch.int32, device=self.dev)
         self.rbits = None
-        if want_dp and int(self.ps[2]) <= 64:
+        self.rv = self.rb16 = None
+        # small windows (the 7^3 flylight patches): "received" tables instead of rbits
+        self.small = (int(self.ps[2]) <= 8 and int(self.ps[0] * self.ps[1]) <= 64 and
+                      int(self.kwargs.get('ppp_consensus_impl', 0)) in (0, 4))
+        if want_rbits is None:
+            want_rbits = not self.small
+        if want_dp and self.small:
+            w16 = int(cc.call('ppp_received_row_words', self.cfg))
+            self.rv = torch.empty((F, self.P), dtype=torch.float32, device=self.dev)
+            self.rb16 = torch.empty((F, w16), dtype=torch.int16, device=self.dev)
+        if want_dp and want_rbits and int(self.ps[2]) <= 64:
             self.rbits = torch.empty((int(self.ps[0] * self.ps[1]), F, 2), dtype=torch.int64,
                                      device=self.dev)
         if self.rows is not None:
@@ -203,25 +213,43 @@ class BlockAssembler:
             cc.call('ppp_prepare_patches', cc.ptr(self.pred), cc.ptr(self.flags),
                     cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.dp),
                     cc.ptr(self.fcmask), None, cc.ptr(self.rbits), self.stream)
+        if self.rv is not None:
+            if self.rows is not None:
+                cc.call('ppp_received_rows', cc.ptr(self.rows.patches),
+                        cc.ptr(self.rows.vox2row), cc.ptr(self.flags), cc.ptr(self.rowvox),
+                        self.F, self.cfg, cc.ptr(self.rv), cc.ptr(self.rb16), self.stream)
+            else:
+                cc.call('ppp_received', cc.ptr(self.pred), cc.ptr(self.flags),
+                        cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.rv),
+                        cc.ptr(self.rb16), self.stream)
         self._prepared = True
         return self.F
 
     # -- step 1 ------------------------------------------------------------
-    def consensus(self, want_cnt=False, impl=None):
+    def consensus(self, want_cnt=False, impl=None, need=None):
         """create_consensus_array_cuda (consensus_array.py:71-206).
 
-        impl 0 = automatic (bit-guided gather for psx < 16, tiled TMA kernel
-        otherwise), 1 = simple gather (cross-check), 2 / 3 force one of the two."""
+        impl 0 = automatic (received tables for psx <= 8, bit-guided gather for
+        psx < 16, tiled TMA kernel otherwise), 1 = simple gather (cross-check),
+        2 / 3 force bit-guided / tiled, 4 = received tables.
+        need: u8 [F] device tensor, rows with 0 are skipped (impl 0/4 on small
+        windows only; the other kernels compute every row)."""
         torch = _torch()
         if not self._prepared:
             self.prepare()
         if impl is None:
             impl = int(self.kwargs.get('ppp_consensus_impl', 0))
-        if self.rbits is None:
-            impl = 1
         F = max(self.F, 1)
         self.cons = torch.empty((F, self.K), dtype=torch.float32, device=self.dev)
         self.cnt = torch.empty((F, self.K), dtype=torch.int32, device=self.dev)
+        if self.rv is not None and impl in (0, 4):
+            cc.call('ppp_consensus_small', cc.ptr(self.rv), cc.ptr(self.rb16),
+                    cc.ptr(self.flags), cc.ptr(self.fgidx), cc.ptr(self.rowvox),
+                    cc.ptr(need), self.F, self.cfg, cc.ptr(self.cons), cc.ptr(self.cnt),
+                    self.stream)
+            return self.cons
+        if self.rbits is None:
+            impl = 1
         scratch = torch.empty(cc.call('ppp_consensus_scratch_bytes', self.cfg),
                               dtype=torch.uint8, device=self.dev)
         cc.call('ppp_consensus', cc.ptr(self.dp), cc.ptr(self.rbits), cc.ptr(self.flags),

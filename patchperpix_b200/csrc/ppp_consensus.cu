@@ -289,6 +289,135 @@ consensus_bits_kernel(const float* __restrict__ dp, const unsigned long long* __
 }
 
 // ---------------------------------------------------------------------------
+// small patches from the RECEIVED tables (ppp_received): same slot-per-thread
+// walk as consensus_bits_kernel (same centre order, bit-identical results), but
+// the partner's class bits are ONE contiguous 16-bit row (the 49 words of a 7^3
+// window = 98 bytes) and the two values of a voting centre are rv[b][d] (own
+// row, staged in shared memory) and rv[b'][d - o] (one load from the partner's
+// contiguous row): no fgidx lookups, no dependent gathers into the centre-major
+// patch array.  `need` (u8 [F], may be NULL): rows with 0 are skipped altogether
+// (face regions of the blockwise stitcher only read the rows of their candidates).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+consensus_small_kernel(const float* __restrict__ rv, const uint16_t* __restrict__ rb16, int rbw,
+                       const uint8_t* __restrict__ flags, const int32_t* __restrict__ fgidx,
+                       const int32_t* __restrict__ rowvox, const uint8_t* __restrict__ need,
+                       int64_t F, ppp_cfg cfg, float* __restrict__ cons,
+                       uint32_t* __restrict__ cnt)
+{
+    Geo g = make_geo(cfg);
+    extern __shared__ __align__(16) unsigned char cs_smem[];
+    const int nrw = g.psz * g.psy;
+    float* s_rv = (float*)cs_smem;                               // [P] own received values
+    int32_t* s_prow = (int32_t*)(s_rv + ((g.P + 3) & ~3));       // [K] partner row of a live slot
+    uint16_t* s_k = (uint16_t*)(s_prow + g.K);                   // [K] its slot index
+    uint16_t* s_rb = s_k + g.K;                                  // [nrw] own class bits
+    __shared__ int s_n;
+    const int64_t row = blockIdx.x;
+    if (need != nullptr && !need[row]) return;
+    const int vb = rowvox[row];
+    int bz, by, bx;
+    vox_decode(g, vb, bz, by, bx);
+    const bool gated = (flags[vb] & PPP_FLAG_GATED) != 0;
+    if (gated) {
+        for (int i = threadIdx.x; i < g.P; i += blockDim.x) s_rv[i] = rv[row * g.P + i];
+        for (int i = threadIdx.x; i < nrw; i += blockDim.x) s_rb[i] = rb16[row * rbw + i];
+    }
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int k0 = 0; k0 < g.K; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        int prow = -1;
+        if (k < g.K && gated) {
+            int lin = k + g.K + 1;
+            int ox = lin % g.nx - (g.psx - 1);
+            int t = lin / g.nx;
+            int oy = t % g.ny - (g.psy - 1);
+            int oz = t / g.ny - (g.psz - 1);
+            int pz = bz + oz, py = by + oy, px = bx + ox;
+            if (pz >= 0 && pz < g.Z && py >= 0 && py < g.Y && px >= 0 && px < g.X) {
+                int vp = (pz * g.Y + py) * g.X + px;
+                if (flags[vp] & PPP_FLAG_GATED) prow = fgidx[vp];
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, prow >= 0);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_n, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (prow >= 0) {
+            int idx = base + __popc(bal & ((1u << lane) - 1u));
+            s_prow[idx] = prow;
+            s_k[idx] = (uint16_t)k;
+        } else if (k < g.K) {
+            cnt[row * g.K + k] = 0;
+            cons[row * g.K + k] = 0.0f;
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    const unsigned xmask = (1u << g.psx) - 1u;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int k = s_k[idx];
+        const int64_t pr = s_prow[idx];
+        const uint16_t* __restrict__ rbp = rb16 + pr * rbw;
+        const float* __restrict__ rvp = rv + pr * g.P;
+        int lin = k + g.K + 1;
+        int ox = lin % g.nx - (g.psx - 1);
+        int t = lin / g.nx;
+        int oy = t % g.ny - (g.psy - 1);
+        int oz = t / g.ny - (g.psz - 1);
+        int pos = 0, neg = 0;
+        float sum = 0.0f;
+        int dz0 = max(-g.rz, oz - g.rz), dz1 = min(g.rz, oz + g.rz);
+        int dy0 = max(-g.ry, oy - g.ry), dy1 = min(g.ry, oy + g.ry);
+        for (int dz = dz0; dz <= dz1; dz++)
+        for (int dy = dy0; dy <= dy1; dy++) {
+            const int w1 = (dz + g.rz) * g.psy + (dy + g.ry);
+            const int w2 = (dz - oz + g.rz) * g.psy + (dy - oy + g.ry);
+            const unsigned a = s_rb[w1], b = __ldg(rbp + w2);
+            const unsigned h1 = a & 0xffu, l1 = a >> 8;
+            unsigned h2 = b & 0xffu, l2 = b >> 8;
+            if (ox >= 0) { h2 = (h2 << ox) & xmask; l2 = (l2 << ox) & xmask; }
+            else { h2 >>= -ox; l2 >>= -ox; }
+            pos += __popc(h1 & h2);
+            neg += __popc(h1 & l2) + __popc(l1 & h2);
+            unsigned m = (h1 & (h2 | l2)) | (l1 & h2);           // centres that vote
+            if (!m || cfg.prod_mode == 0) continue;
+            const float* __restrict__ r1 = s_rv + w1 * g.psx;
+            const float* __restrict__ r2 = rvp + w2 * g.psx - ox;
+            while (m) {
+                const int tb = __ffs((int)m) - 1;
+                m &= m - 1;
+                sum = fmaf(r1[tb], __ldg(r2 + tb), sum);
+            }
+        }
+        cons[row * g.K + k] = consensus_epilogue(cfg, sum, pos, neg);
+        cnt[row * g.K + k] = ((uint32_t)neg << 16) | (uint32_t)pos;
+    }
+}
+
+extern "C" int ppp_consensus_small(const float* rv, const uint16_t* rb16, const uint8_t* flags,
+                                   const int32_t* fgidx, const int32_t* rowvox,
+                                   const uint8_t* need, int64_t F, const ppp_cfg* cfg,
+                                   float* cons, uint32_t* cnt, void* stream)
+{
+    if (F <= 0) return 0;
+    Geo g = make_geo(*cfg);
+    if (g.psx > 8 || g.psz * g.psy > 64)
+        return ppp_fail(-1, "ppp_consensus_small: window too large (psx <= 8, psz*psy <= 64)");
+    if (g.K > 65535) return ppp_fail(-1, "ppp_consensus_small: more than 65535 offsets");
+    const int rbw = ((g.psz * g.psy + 7) / 8) * 8;
+    size_t sm = (size_t)((g.P + 3) & ~3) * 4 + (size_t)g.K * 6 + (size_t)g.psz * g.psy * 2 + 16;
+    cudaError_t e = cudaFuncSetAttribute(consensus_small_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return ppp_fail((int)e, "ppp_consensus_small: smem attribute");
+    consensus_small_kernel<<<(unsigned)F, 128, sm, (cudaStream_t)stream>>>(
+        rv, rb16, rbw, flags, fgidx, rowvox, need, F, *cfg, cons, cnt);
+    return ppp_check("ppp_consensus_small");
+}
+
+// ---------------------------------------------------------------------------
 // sums.  CTA = (base line, group of NOY consecutive offset rows (oz,oy)).
 //
 // Rows of `dp` are in raster order, so the valid centres of a line are a

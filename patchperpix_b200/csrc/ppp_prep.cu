@@ -381,3 +381,94 @@ extern "C" int ppp_prepare_rows(const uint16_t* patches, const int32_t* vox2row,
     }
     return ppp_check("ppp_prepare_rows");
 }
+
+// ---------------------------------------------------------------------------
+// "received" patches for small windows (psx <= 8, e.g. the 7^3 flylight patches):
+// for every gated voxel b the class-folded value EVERY surrounding centre assigns
+// to it, rv[row(b)][d] = D_{b+d}(b) with d in window raster order (0 where b+d is
+// no patch centre), and the class bits of the same table packed per centre line:
+// rb16[row][w] = (L bits << 8) | H bits, bit t <-> centre b + (dz, dy, t - rx).
+// The consensus of a voxel pair is then a masked dot product of two such rows
+// (ppp_consensus_small): partner data is one contiguous row instead of gathers
+// through fgidx into the centre-major array.  One warp per row.
+// ---------------------------------------------------------------------------
+template <class Src>
+__global__ void __launch_bounds__(256)
+received_values_kernel(Src src, const uint8_t* __restrict__ flags,
+                       const int32_t* __restrict__ rowvox, int64_t F, ppp_cfg cfg,
+                       float* __restrict__ rv, uint16_t* __restrict__ rb16, int rbw)
+{
+    Geo g = make_geo(cfg);
+    __shared__ unsigned s_bits[8][64];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 8 + w;
+    if (row >= F) return;
+    const int nrw = g.psz * g.psy;
+    const int v = rowvox[row];
+    for (int i = lane; i < 64; i += 32) s_bits[w][i] = 0u;
+    __syncwarp();
+    if (flags[v] & PPP_FLAG_GATED) {
+        int bz, by, bx;
+        vox_decode(g, v, bz, by, bx);
+        for (int base = 0; base < g.P; base += 32) {
+            const int d = base + lane;
+            if (d < g.P) {
+                int qz, qy, qx;
+                po_decode(g, d, qz, qy, qx);
+                const int cz = bz + qz - g.rz, cy = by + qy - g.ry, cx = bx + qx - g.rx;
+                float val = 0.0f;
+                if (cz >= g.rz && cz < g.Z - g.rz && cy >= g.ry && cy < g.Y - g.ry &&
+                    cx >= g.rx && cx < g.X - g.rx) {
+                    const int64_t vc = ((int64_t)cz * g.Y + cy) * g.X + cx;
+                    if (flags[vc] & PPP_FLAG_CENTRE)    // b seen from c sits at patch index r - d
+                        val = fold_class(src.at(g.P - 1 - d, vc), cfg.th_gt, cfg.bg_lt);
+                }
+                rv[row * g.P + d] = val;
+                if (val > 0.0f) atomicOr(&s_bits[w][qz * g.psy + qy], 1u << qx);
+                else if (val < 0.0f) atomicOr(&s_bits[w][qz * g.psy + qy], 256u << qx);
+            }
+        }
+        __syncwarp();
+    }
+    for (int i = lane; i < rbw; i += 32)
+        rb16[row * rbw + i] = (uint16_t)(i < nrw ? s_bits[w][i] : 0u);
+}
+
+static int received_check(const Geo& g, int64_t F)
+{
+    if (g.psx > 8) return ppp_fail(-1, "ppp_received: psx > 8 (use the rbits path)");
+    if (g.psz * g.psy > 64) return ppp_fail(-1, "ppp_received: more than 64 centre lines");
+    if (F * (int64_t)g.P > 0x7fffffffffLL) return ppp_fail(-1, "ppp_received: too many rows");
+    return 0;
+}
+
+extern "C" int32_t ppp_received_row_words(const ppp_cfg* cfg)
+{
+    Geo g = make_geo(*cfg);
+    return ((g.psz * g.psy + 7) / 8) * 8;
+}
+
+extern "C" int ppp_received(const float* pred, const uint8_t* flags, const int32_t* rowvox,
+                            int64_t F, const ppp_cfg* cfg, float* rv, uint16_t* rb16,
+                            void* stream)
+{
+    if (F <= 0) return 0;
+    Geo g = make_geo(*cfg);
+    if (int rc = received_check(g, F)) return rc;
+    received_values_kernel<SrcDense><<<(unsigned)((F + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        SrcDense{pred, g.V}, flags, rowvox, F, *cfg, rv, rb16, ppp_received_row_words(cfg));
+    return ppp_check("ppp_received");
+}
+
+extern "C" int ppp_received_rows(const uint16_t* patches, const int32_t* vox2row,
+                                 const uint8_t* flags, const int32_t* rowvox, int64_t F,
+                                 const ppp_cfg* cfg, float* rv, uint16_t* rb16, void* stream)
+{
+    if (F <= 0) return 0;
+    Geo g = make_geo(*cfg);
+    if (int rc = received_check(g, F)) return rc;
+    received_values_kernel<SrcRows><<<(unsigned)((F + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        SrcRows{(const __half*)patches, vox2row, g.P}, flags, rowvox, F, *cfg, rv, rb16,
+        ppp_received_row_words(cfg));
+    return ppp_check("ppp_received_rows");
+}

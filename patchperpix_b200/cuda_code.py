@@ -128,6 +128,10 @@ _SIGS = {
     'ppp_paint': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
     'ppp_paint_channels': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
     'ppp_paint_patches': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
+    'ppp_received_row_words': (ctypes.c_int32, ['cfg']),
+    'ppp_received': (ctypes.c_int, ['p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
+    'ppp_received_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
+    'ppp_consensus_small': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
     'ppp_gate_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'cfg', 'p', 'p']),
     'ppp_prepare_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p', 'p', 'p']),
     'ppp_patch_graph_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),

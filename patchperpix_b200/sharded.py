@@ -398,19 +398,31 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
         raise ValueError("coordinate %d outside every slab" % coord)
     owner = [slab_of(int(o[axis])) for o in offsets]
 
+    import time
+    tm = {}
+    t_last = [time.perf_counter()]
+
+    def lap(name):
+        if kwargs.get('ppp_phase_sync', True):
+            torch.cuda.synchronize() if shard.dev.type == 'cuda' else None
+        now = time.perf_counter()
+        tm[name] = tm.get(name, 0.0) + (now - t_last[0]) * 1e3
+        t_last[0] = now
+
     # ---- exchange (0): halo rows ---------------------------------------------------
     halo = int(2 * ps[axis] + ps[axis] // 2)
     shard.exchange_halo(slabs, halo)
+    lap('halo_exchange')
 
     # ---- phase 1: the blocks of my slab ----------------------------------------------
     my_blocks = [b for b in range(nblk) if owner[b] == rank]
     res = _run_jobs(my_blocks, lambda b: _block_job(shard, offsets[b], chunksize, ps, kwargs, block_fn),
                     workers)
     mine = {b: r for b, r in zip(my_blocks, res) if r is not None}
+    lap('blocks')
     blocks = _allgather_edges(mine, nblk, lambda b: owner[b])       # exchange (1)
+    lap('allgather_block_edges')
     selected = {}
-    for b, (p, _) in blocks.items():
-        selected[b] = np.unique(p.reshape(-1, 3).astype(np.int64), axis=0)   # :166-171
 
     # ---- phase 2: face jobs, on the owner of the higher block ------------------------
     key_of = {tuple(int(v) for v in o): i for i, o in enumerate(offsets)}
@@ -427,9 +439,21 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
                 continue
             jobs.append((b, nb, dim))
 
+    sel_lock = threading.Lock()
+
+    def selected_of(b):
+        """the selected patches of a block = the nodes of its pair list (:166-171)"""
+        with sel_lock:
+            if b not in selected:
+                p = blocks[b][0].reshape(-1, 3).astype(np.int64)
+                key = (p[:, 0] * shape[1] + p[:, 1]) * shape[2] + p[:, 2]
+                _, first = np.unique(key, return_index=True)     # sorted by (z,y,x) like
+                selected[b] = p[first]                           # np.unique(axis=0)
+            return selected[b]
+
     def face(j):
         b, nb, dim = jobs[j]
-        cur, nbc = face_candidates(selected[b], selected[nb], offsets[b], dim, ps)
+        cur, nbc = face_candidates(selected_of(b), selected_of(nb), offsets[b], dim, ps)
         if len(cur) == 0 or len(nbc) == 0:
             return None
         cands, pa = face_pairs(cur, nbc, ps)
@@ -439,7 +463,9 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
     my_jobs = [j for j in range(len(jobs)) if owner[jobs[j][0]] == rank]
     res = _run_jobs(my_jobs, face, workers)
     my_faces = {j: r for j, r in zip(my_jobs, res) if r is not None}
+    lap('faces')
     faces = _allgather_edges(my_faces, len(jobs), lambda j: owner[jobs[j][0]])  # exchange (2)
+    lap('allgather_face_edges')
 
     # ---- the global edge list in the reference's order (update_graph calls) -----------
     plist, alist = [], []
@@ -457,6 +483,7 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
                 alist.append(faces[j][1])
     info = dict(n_blocks=nblk, n_faces=len(jobs), n_edges=int(sum(len(a) for a in alist)),
                 my_blocks=len(my_blocks), my_faces=len(my_jobs), halo_bytes=shard.halo_bytes,
+                phase_ms=tm,
                 rows=int(shard.coords.shape[0]), own_rows=shard.n_own)
     own_box = list(shape)
     own_box[axis] = shard.hi - shard.lo
@@ -471,8 +498,10 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
     # ---- phase 3: replicated partition, painting of my slab --------------------------
     if paint_fn is not None:
         return paint_fn(shard, pairs, aff, own_box, **kwargs), info
+    lap('edge_list')
     node_coords, label, n_labels = partition_graph(pairs, aff, shape, shard.dev, **kwargs)
     info['n_labels'] = n_labels
+    lap('partition')
     r_ax = int(ps[axis] // 2)
     a = node_coords[:, axis]
     near = (a >= max(shard.lo - r_ax, shard.ext_lo)) & (a < min(shard.hi + r_ax, shard.ext_hi)) \
@@ -490,6 +519,7 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
         cc.call('ppp_paint_rows', cc.ptr(shard.patches), cc.ptr(node_row),
                 cc.ptr(zyx.contiguous()), cc.ptr(label[sel].contiguous()), int(sel.numel()),
                 cfg, cc.ptr(inst), cc.current_stream_ptr())
+    lap('paint')
     return inst, info
 
 

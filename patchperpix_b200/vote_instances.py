@@ -145,7 +145,22 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
 
     # (1) consensus
     if not kwargs.get('skipConsensus', False):
-        asm.consensus()
+        need = None
+        if kwargs.get('selected_patches') is not None and kwargs.get('skipRanking', False) \
+                and kwargs.get('selected_patch_pairs') is not None and asm.small:
+            # stitcher's face job (stitch_patch_graph.py:323-328): only the patch graph of the
+            # given pairs reads the consensus, i.e. rows inside the windows of those patches
+            sc = torch.from_numpy(np.asarray(kwargs['selected_patches'],
+                                             dtype=np.int64).reshape(-1, 3)).to(asm.dev)
+            ok = ((sc >= 0) & (sc < torch.tensor(shape, device=asm.dev))).all(dim=1)
+            sc = sc[ok]
+            seed = torch.zeros((1, 1) + shape, dtype=torch.float32, device=asm.dev)
+            seed[0, 0, sc[:, 0], sc[:, 1], sc[:, 2]] = 1.0
+            win = torch.nn.functional.max_pool3d(
+                seed, kernel_size=tuple(int(p) for p in patchshape), stride=1,
+                padding=tuple(int(r) for r in rad))
+            need = win.reshape(-1)[asm.rowvox.long()].to(torch.uint8).contiguous()
+        asm.consensus(need=need)
     if kwargs.get('save_consensus', False):
         return None, None
     # (2) ranking
