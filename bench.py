@@ -5,7 +5,7 @@ Workload = BASELINE.json configs[4] (the north-star volume): ONE FlyLight-sized
 3-D volume, 256x1024x1024, patchshape 7x7x7, synthetic neurites (seeded,
 patchperpix_b200/synth.py), predictions in the compact row form a ppp+dec run
 produces (float16 [G][343] for the G foreground voxels), assembled BLOCKWISE
-(chunks 128^3 + patchshape//2 halo, one job per shared face, one global
+(chunks 128x64x256 + patchshape//2 halo, one job per shared face, one global
 partition) through patchperpix_b200.sharded.stitch_shard.  flylight
 [vote_instances] flags, thresholded connected components.
 
@@ -40,7 +40,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(shape=(256, 1024, 1024), patchshape=(7, 7, 7), chunksize=(128, 128, 128),
+WORKLOAD = dict(shape=(256, 1024, 1024), patchshape=(7, 7, 7), chunksize=(128, 64, 256),
                 seed=4, n=600, seg_len=24.0, n_seg=40)
 CPU_SAMPLE = (72, 72, 72)       # region the CPU arm works on (prebuilt oracle/_ref shapes)
 KW = dict(patch_threshold=0.5, fc_threshold=0.5, cuda=True, blockwise=True,
@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([s.strip() for s in out.split(',')])
             except Exception:
                 pass
-            self.stop_ev.wait(0.2)
+            self.stop_ev.wait(0.5)
 
     def summary(self):
         self.stop_ev.set()
@@ -251,6 +251,7 @@ class CallTimer:
         self.orig = cc.call
         self.ev = []
         self.calls = {}
+        self.needed = []        # rows a masked consensus call really computes
 
     def __enter__(self):
         def timed(name, *a):
@@ -263,17 +264,22 @@ class CallTimer:
             r = self.orig(name, *a)
             e1.record()
             units = 0
-            if name in ('ppp_consensus', 'ppp_rank'):
+            if name == 'ppp_consensus_small':
+                need, name = a[5], 'ppp_consensus'
+                units = int(self.needed.pop())
+            elif name in ('ppp_consensus', 'ppp_rank'):
                 units = int(a[5] if name == 'ppp_consensus' else a[4])
             elif name in ('ppp_patch_graph', 'ppp_patch_graph_rows'):
-                units = int(a[5] if name == 'ppp_patch_graph' else a[6])
+                units = int(a[5] if name == 'ppp_patch_graph' else a[7])
             self.ev.append((name, e0, e1, units))
             return r
         self.cc.call = timed
+        self.cc.profile_hook = lambda name, v: self.needed.append(v)
         return self
 
     def __exit__(self, *exc):
         self.cc.call = self.orig
+        self.cc.profile_hook = None
         self.torch.cuda.synchronize()
         for name, e0, e1, units in self.ev:
             d = self.calls.setdefault(name, dict(ms=0.0, calls=0, units=0))
@@ -292,7 +298,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--shape', default=None, help='z,y,x (default: the FlyLight-sized volume)')
     ap.add_argument('--chunk', default=None, help='z,y,x chunksize')
-    ap.add_argument('--workers', type=int, default=3)
+    ap.add_argument('--workers', type=int, default=6)
     ap.add_argument('--mws', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -316,13 +322,22 @@ def main():
     _, P, _, _, _, K = patch_geometry(ps)
     kw = dict(KW, patchshape=list(w['patchshape']), chunksize=list(w['chunksize']), mws=args.mws)
     shape = w['shape']
-    axis, slabs = sharded.slab_partition(shape, w['chunksize'], world)
-    lo, hi = slabs[rank]
 
     # ---- inputs: the patch rows of my slab, resident in HBM ---------------------
+    # slabs = contiguous runs of block rows balanced by their foreground count (every
+    # rank draws the same label volume; a production run would histogram its fg mask)
     t_gen = time.perf_counter()
+    vol = synth.neurites_3d(shape, **synth_kw(w))
+    axis, _ = sharded.slab_partition(shape, w['chunksize'], world)
+    csz = min(w['chunksize'][axis], shape[axis])
+    per_plane = (vol[0] > 0).sum(axis=tuple(a for a in range(3) if a != axis))
+    weights = [int(per_plane[i:i + csz].sum()) for i in range(0, shape[axis], csz)]
+    axis, slabs = sharded.slab_partition(shape, w['chunksize'], world, axis=axis,
+                                         weights=weights)
+    lo, hi = slabs[rank]
     coords, patches, numinst = synth.neurite_rows(shape, ps, axis=axis, lo=lo, hi=hi,
-                                                  device=dev, **synth_kw(w))
+                                                  device=dev, volume=vol, **synth_kw(w))
+    del vol
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
     n_own = int(coords.shape[0])
@@ -340,8 +355,9 @@ def main():
     # ---- device-resident timing -------------------------------------------------
     for _ in range(warm):
         inst, info = device_step()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local) if rank == 0 else None     # one nvidia-smi poller per box
+    if sampler:
+        sampler.start()
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
@@ -353,7 +369,7 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - tw) * 1e3 / steps
     ms = t0.elapsed_time(t1) / steps
-    clocks = sampler.summary()
+    clocks = sampler.summary() if sampler else None
 
     # ---- end to end: pinned host rows -> uint16 labels of my slab on the host ------
     coords_h = coords.cpu().pin_memory()
@@ -443,7 +459,7 @@ def main():
         unit='Mvoxels/s', n_gpus=world, steps=steps, warmup=warm, ms_per_step=ms,
         higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32',
         data='synthetic',
-        config=dict(workload=workload_name(w), fg_voxels=tot_fg, slab_axis=axis,
+        config=dict(workload=workload_name(w), fg_voxels=tot_fg, slab_axis=axis, slabs=slabs,
                     blocks=info['n_blocks'], faces=info['n_faces'], edges=info['n_edges'],
                     instances=n_inst, labels_sha1=sha, block_workers=args.workers,
                     halo_bytes_per_step=halo,

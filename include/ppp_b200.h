@@ -122,12 +122,15 @@ int ppp_consensus(const float* dp, const uint64_t* rbits, const uint8_t* flags,
  * (dz,dy) = (background bits << 8) | high bits of the same table.
  * ppp_consensus_small gives bit-identical cons / cnt to ppp_consensus (same
  * centre order).  need u8 [F] or NULL: rows with 0 are skipped and left
- * unwritten (callers that only read the rows of known patches). */
-int32_t ppp_received_row_words(const ppp_cfg* cfg);
+ * unwritten (callers that only read the rows of known patches; the tables must
+ * then cover those rows AND their partners, i.e. the mask dilated by 2*ps-1). */
+int64_t ppp_received_row_words(const ppp_cfg* cfg);
 int ppp_received(const float* pred, const uint8_t* flags, const int32_t* rowvox,
-                 int64_t F, const ppp_cfg* cfg, float* rv, uint16_t* rb16, void* stream);
+                 const uint8_t* need, int64_t F, const ppp_cfg* cfg, float* rv,
+                 uint16_t* rb16, void* stream);
 int ppp_received_rows(const uint16_t* patches, const int32_t* vox2row,
-                      const uint8_t* flags, const int32_t* rowvox, int64_t F,
+                      const uint8_t* flags, const int32_t* rowvox,
+                      const uint8_t* need, int64_t F,
                       const ppp_cfg* cfg, float* rv, uint16_t* rb16, void* stream);
 int ppp_consensus_small(const float* rv, const uint16_t* rb16, const uint8_t* flags,
                         const int32_t* fgidx, const int32_t* rowvox,
@@ -249,9 +252,14 @@ int ppp_prepare_rows(const uint16_t* patches, const int32_t* vox2row,
                      const uint8_t* flags, const int32_t* rowvox, int64_t F,
                      const ppp_cfg* cfg, float* dp, uint32_t* fcmask,
                      uint32_t* ptmask, uint64_t* rbits, void* stream);
+/* pair_org i32 [n][3] or NULL: origin of the region the reference handed pair i to its
+ * kernel in (the sub-sampling seed is the product of the REGION-relative centre
+ * coordinates, computePatchGraph.cu:24-27); lets the cross pairs of many face regions
+ * (stitch_patch_graph.py:252-336) run as one launch over one shared region. */
 int ppp_patch_graph_rows(const uint16_t* patches, const int32_t* vox2row,
                          const uint8_t* flags, const int32_t* fgidx,
-                         const float* cons, const uint32_t* pairs, int64_t n,
+                         const float* cons, const uint32_t* pairs,
+                         const int32_t* pair_org, int64_t n,
                          const ppp_cfg* cfg, float* aff, void* scratch, void* stream);
 /* painting of graph nodes into a sub-volume `instances` i32 [cfg Z][Y][X] (zeroed
  * by the caller): node i has its centre at node_zyx[i] (coordinates of that

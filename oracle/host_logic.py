@@ -255,7 +255,8 @@ def assemble(pred, foreground, numinst, patchshape, kw, kern):
     out['ranked'] = np.array([p[0] for p in ranked], np.int32).reshape(-1, 3)
     fc = np.float32(kw['fc_threshold'])
     sel = foreground_cover(overlap_mask, mask, ps, ranked, rad, pred, fc,
-                           sparse=kw['select_patches_for_sparse_data'])
+                           sparse=kw['select_patches_for_sparse_data'],
+                           score_threshold=kw.get('score_threshold'))
     out['cover'] = np.array([p[0] for p in sel], np.int32).reshape(-1, 3)
     if not kw.get('skipThinCover', False) and len(sel) > 0:
         sel = thin_cover(mask, sel, ps, rad, pred, fc)

@@ -128,6 +128,22 @@ class RowSource:
         return out
 
 
+_HP_STREAMS = {}
+
+
+def _latency_stream(cur):
+    """high-priority companion of stream `cur` (created once per stream): the few-CTA,
+    latency-bound stages (thinning rounds, cover, the candidate sort) are launched on it,
+    so that the block scheduler slots their CTAs in ahead of the large grids that other
+    host threads (other blocks) have in flight instead of queueing behind them."""
+    torch = _torch()
+    key = (cur.device.index, cur.cuda_stream)
+    if key not in _HP_STREAMS:
+        lo, hi = torch.cuda.Stream.priority_range()
+        _HP_STREAMS[key] = torch.cuda.Stream(cur.device, priority=hi)
+    return _HP_STREAMS[key]
+
+
 class BlockAssembler:
     """state of one block on the device.
 
@@ -158,14 +174,26 @@ class BlockAssembler:
         self.foreground = foreground.to(torch.uint8).contiguous()
         self.overlap = overlap.to(torch.uint8).contiguous()
         self.stream = cc.current_stream_ptr()
+        self._cur = torch.cuda.current_stream()
+        self._hp = _latency_stream(self._cur) if kwargs.get('ppp_latency_stream', True) else None
         self.W = (self.P + 31) // 32
         self.cons = None
         self.cnt = None
         self.score = None
         self._prepared = False
 
+    def _latency(self, fn):
+        """run fn(stream pointer) on the high-priority companion stream, ordered after
+        everything queued on the block's stream and before everything that follows."""
+        if self._hp is None:
+            return fn(self.stream)
+        self._hp.wait_stream(self._cur)
+        r = fn(ctypes.c_void_p(self._hp.cuda_stream))
+        self._cur.wait_stream(self._hp)
+        return r
+
     # -- step 0 ------------------------------------------------------------
-    def prepare(self, want_dp=True, want_rbits=None):
+    def prepare(self, want_dp=True, want_rbits=None, want_rv=None, want_masks=True):
         torch = _torch()
         V = self.V
         self.flags = torch.empty(V, dtype=torch.uint8, device=self.dev)
@@ -190,7 +218,8 @@ class BlockAssembler:
         rsg = ((int(self.ps[2]) + 16 + 3) // 4) * 4
         self.dp = torch.zeros((F, int(self.ps[0] * self.ps[1]) * rsg), dtype=torch.float32,
                               device=self.dev) if want_dp else None
-        self.fcmask = torch.empty((F, self.W), dtype=torch.int32, device=self.dev)
+        self.fcmask = torch.empty((F, self.W), dtype=torch.int32, device=self.dev) \
+            if want_masks else None
         self.rbits = None
         self.rv = self.rb16 = None
         # small windows (the 7^3 flylight patches): "received" tables instead of rbits
@@ -198,32 +227,42 @@ class BlockAssembler:
                       int(self.kwargs.get('ppp_consensus_impl', 0)) in (0, 4))
         if want_rbits is None:
             want_rbits = not self.small
-        if want_dp and self.small:
-            w16 = int(cc.call('ppp_received_row_words', self.cfg))
-            self.rv = torch.empty((F, self.P), dtype=torch.float32, device=self.dev)
-            self.rb16 = torch.empty((F, w16), dtype=torch.int16, device=self.dev)
+        if want_rv is None:
+            want_rv = self.small
         if want_dp and want_rbits and int(self.ps[2]) <= 64:
             self.rbits = torch.empty((int(self.ps[0] * self.ps[1]), F, 2), dtype=torch.int64,
                                      device=self.dev)
-        if self.rows is not None:
-            cc.call('ppp_prepare_rows', cc.ptr(self.rows.patches), cc.ptr(self.rows.vox2row),
-                    cc.ptr(self.flags), cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.dp),
-                    cc.ptr(self.fcmask), None, cc.ptr(self.rbits), self.stream)
-        else:
-            cc.call('ppp_prepare_patches', cc.ptr(self.pred), cc.ptr(self.flags),
-                    cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.dp),
-                    cc.ptr(self.fcmask), None, cc.ptr(self.rbits), self.stream)
-        if self.rv is not None:
+        if want_dp or want_masks or self.rbits is not None:
             if self.rows is not None:
-                cc.call('ppp_received_rows', cc.ptr(self.rows.patches),
+                cc.call('ppp_prepare_rows', cc.ptr(self.rows.patches),
                         cc.ptr(self.rows.vox2row), cc.ptr(self.flags), cc.ptr(self.rowvox),
-                        self.F, self.cfg, cc.ptr(self.rv), cc.ptr(self.rb16), self.stream)
+                        self.F, self.cfg, cc.ptr(self.dp), cc.ptr(self.fcmask), None,
+                        cc.ptr(self.rbits), self.stream)
             else:
-                cc.call('ppp_received', cc.ptr(self.pred), cc.ptr(self.flags),
-                        cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.rv),
-                        cc.ptr(self.rb16), self.stream)
+                cc.call('ppp_prepare_patches', cc.ptr(self.pred), cc.ptr(self.flags),
+                        cc.ptr(self.rowvox), self.F, self.cfg, cc.ptr(self.dp),
+                        cc.ptr(self.fcmask), None, cc.ptr(self.rbits), self.stream)
+        if want_rv and self.small:
+            self.received()
         self._prepared = True
         return self.F
+
+    def received(self, need=None):
+        """the "received" tables of the small-window consensus (ppp_received); need: u8
+        [F], rows with 0 are skipped (must cover the wanted rows and their partners)."""
+        torch = _torch()
+        F = max(self.F, 1)
+        w16 = int(cc.call('ppp_received_row_words', self.cfg))
+        self.rv = torch.empty((F, self.P), dtype=torch.float32, device=self.dev)
+        self.rb16 = torch.empty((F, w16), dtype=torch.int16, device=self.dev)
+        if self.rows is not None:
+            cc.call('ppp_received_rows', cc.ptr(self.rows.patches), cc.ptr(self.rows.vox2row),
+                    cc.ptr(self.flags), cc.ptr(self.rowvox), cc.ptr(need), self.F, self.cfg,
+                    cc.ptr(self.rv), cc.ptr(self.rb16), self.stream)
+        else:
+            cc.call('ppp_received', cc.ptr(self.pred), cc.ptr(self.flags), cc.ptr(self.rowvox),
+                    cc.ptr(need), self.F, self.cfg, cc.ptr(self.rv), cc.ptr(self.rb16),
+                    self.stream)
 
     # -- step 1 ------------------------------------------------------------
     def consensus(self, want_cnt=False, impl=None, need=None):
@@ -243,13 +282,19 @@ class BlockAssembler:
         self.cons = torch.empty((F, self.K), dtype=torch.float32, device=self.dev)
         self.cnt = torch.empty((F, self.K), dtype=torch.int32, device=self.dev)
         if self.rv is not None and impl in (0, 4):
+            if cc.profile_hook is not None:
+                cc.profile_hook('consensus_rows',
+                                self.F if need is None else int(need.sum().item()))
             cc.call('ppp_consensus_small', cc.ptr(self.rv), cc.ptr(self.rb16),
                     cc.ptr(self.flags), cc.ptr(self.fgidx), cc.ptr(self.rowvox),
                     cc.ptr(need), self.F, self.cfg, cc.ptr(self.cons), cc.ptr(self.cnt),
                     self.stream)
             return self.cons
-        if self.rbits is None:
-            impl = 1
+        Z, Y, X = self.shape
+        if self.rbits is None or (impl in (0, 3) and int(self.ps[2]) >= 16 and
+                                  (X > 2048 or int(self.ps[0] * self.ps[1]) > 128)) \
+                or self.K > 65535:
+            impl = 1        # the simple gather has none of the tiled kernels' limits
         scratch = torch.empty(cc.call('ppp_consensus_scratch_bytes', self.cfg),
                               dtype=torch.uint8, device=self.dev)
         cc.call('ppp_consensus', cc.ptr(self.dp), cc.ptr(self.rbits), cc.ptr(self.flags),
@@ -285,14 +330,19 @@ class BlockAssembler:
         order = torch.empty(max(n, 1), dtype=torch.int32, device=self.dev)
         scratch = torch.empty(cc.call('ppp_rank_sort_scratch_bytes', n), dtype=torch.uint8,
                               device=self.dev)
-        cc.call('ppp_rank_sort', cc.ptr(score), cc.ptr(cand), n, cc.ptr(order),
-                cc.ptr(scratch), self.stream)
+        self._latency(lambda st: cc.call('ppp_rank_sort', cc.ptr(score), cc.ptr(cand), n,
+                                         cc.ptr(order), cc.ptr(scratch), st))
         return order[:n]
 
     # -- steps 3+4 ---------------------------------------------------------
     def cover(self, mask, order):
         """computeForegroundCover (foreground_cover.py:15-180)."""
         torch = _torch()
+        # score_threshold (foreground_cover.py:136-138): the walk stops at the first ranked
+        # patch whose score is below it -- scores are sorted, so the list is cut there
+        if isinstance(self.kwargs.get('score_threshold', False), float) and order.numel():
+            sc = self.score.reshape(-1)[order.long()].double()
+            order = order[:int((sc >= self.kwargs['score_threshold']).sum().item())].contiguous()
         n = int(order.numel())
         if n == 0:
             return order
@@ -310,9 +360,10 @@ class BlockAssembler:
         scratch = torch.empty(cc.call('ppp_cover_scratch_bytes', self.cfg),
                               dtype=torch.uint8, device=self.dev)
         mask = mask.to(torch.uint8).contiguous()
-        cc.call('ppp_cover', cc.ptr(mask), cc.ptr(self.overlap), cc.ptr(order), n,
-                cc.ptr(self.fgidx), cc.ptr(self.fcmask), self.cfg, cc.ptr(pix_t),
-                len(pix), cc.ptr(selected), cc.ptr(scratch), self.stream)
+        self._latency(lambda st: cc.call(
+            'ppp_cover', cc.ptr(mask), cc.ptr(self.overlap), cc.ptr(order), n,
+            cc.ptr(self.fgidx), cc.ptr(self.fcmask), self.cfg, cc.ptr(pix_t),
+            len(pix), cc.ptr(selected), cc.ptr(scratch), st))
         return order[selected.bool()]
 
     def thin(self, mask, sel):
@@ -326,8 +377,9 @@ class BlockAssembler:
                               dtype=torch.uint8, device=self.dev)
         mask = mask.to(torch.uint8).contiguous()
         sel = sel.contiguous()
-        cc.call('ppp_thin', cc.ptr(mask), cc.ptr(sel), m, cc.ptr(self.fgidx),
-                cc.ptr(self.fcmask), self.cfg, cc.ptr(keep), cc.ptr(scratch), self.stream)
+        self._latency(lambda st: cc.call(
+            'ppp_thin', cc.ptr(mask), cc.ptr(sel), m, cc.ptr(self.fgidx),
+            cc.ptr(self.fcmask), self.cfg, cc.ptr(keep), cc.ptr(scratch), st))
         return sel[keep.bool()]
 
     # -- step 4b (host) ------------------------------------------------------
@@ -367,7 +419,7 @@ class BlockAssembler:
         return arr
 
     # -- step 5 ------------------------------------------------------------
-    def patch_graph(self, pairs_dev, fast=None):
+    def patch_graph(self, pairs_dev, fast=None, pair_org=None):
         """computePatchGraph_cuda (aff_patch_graph.py:113-187), matrix form.
         fast=True: parallel double-precision sum instead of the reference's
         serial float order (kwargs ppp_graph_fast)."""
@@ -382,8 +434,9 @@ class BlockAssembler:
         if self.rows is not None:
             cc.call('ppp_patch_graph_rows', cc.ptr(self.rows.patches), cc.ptr(self.rows.vox2row),
                     cc.ptr(self.flags), cc.ptr(self.fgidx), cc.ptr(self.cons), cc.ptr(pairs_dev),
-                    n, cfg, cc.ptr(aff), cc.ptr(scratch), self.stream)
+                    cc.ptr(pair_org), n, cfg, cc.ptr(aff), cc.ptr(scratch), self.stream)
         else:
+            assert pair_org is None, "pair_org needs the compact row form"
             cc.call('ppp_patch_graph', cc.ptr(self.pred), cc.ptr(self.flags),
                     cc.ptr(self.fgidx), cc.ptr(self.cons), cc.ptr(pairs_dev), n, cfg,
                     cc.ptr(aff), cc.ptr(scratch), self.stream)

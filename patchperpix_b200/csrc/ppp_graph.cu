@@ -84,7 +84,8 @@ template <class Src>
 __global__ void __launch_bounds__(PG_THREADS)
 patch_graph_kernel(Src pred, const uint8_t* __restrict__ flags,
                    const int32_t* __restrict__ fgidx, const float* __restrict__ cons,
-                   const uint32_t* __restrict__ pairs, ppp_cfg cfg, float* __restrict__ aff)
+                   const uint32_t* __restrict__ pairs, ppp_cfg cfg, float* __restrict__ aff,
+                   const int32_t* __restrict__ pair_org)
 {
     Geo g = make_geo(cfg);
     extern __shared__ unsigned char smem_raw[];
@@ -100,8 +101,10 @@ patch_graph_kernel(Src pred, const uint8_t* __restrict__ flags,
     const int64_t id = blockIdx.x;
     const int z1c = pairs[id * 6], y1c = pairs[id * 6 + 1], x1c = pairs[id * 6 + 2];
     const int z2c = pairs[id * 6 + 3], y2c = pairs[id * 6 + 4], x2c = pairs[id * 6 + 5];
-    const uint32_t rnd0 = (uint32_t)z1c * (uint32_t)z2c * (uint32_t)y1c * (uint32_t)y2c *
-                          (uint32_t)x1c * (uint32_t)x2c;
+    const int oz_ = pair_org ? pair_org[id * 3] : 0, oy_ = pair_org ? pair_org[id * 3 + 1] : 0,
+              ox_ = pair_org ? pair_org[id * 3 + 2] : 0;
+    const uint32_t rnd0 = (uint32_t)(z1c - oz_) * (uint32_t)(z2c - oz_) * (uint32_t)(y1c - oy_) *
+                          (uint32_t)(y2c - oy_) * (uint32_t)(x1c - ox_) * (uint32_t)(x2c - ox_);
     int ni1, ni2;
     const int n1 = pg_build_list(g, cfg, pred, flags, z1c, y1c, x1c, z2c, y2c, x2c,
                                  s_po1, s_ii1, s_scr1, &ni1);
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(PGR_THREADS)
 patch_graph_ref_kernel(Src pred, const uint8_t* __restrict__ flags,
                        const int32_t* __restrict__ fgidx, const float* __restrict__ cons,
                        const uint32_t* __restrict__ pairs, ppp_cfg cfg, float* __restrict__ aff,
-                       int32_t* __restrict__ lists)
+                       int32_t* __restrict__ lists, const int32_t* __restrict__ pair_org)
 {
     Geo g = make_geo(cfg);
     // the two pixel lists of this pair live in GLOBAL scratch (written once, then read
@@ -264,8 +267,12 @@ patch_graph_ref_kernel(Src pred, const uint8_t* __restrict__ flags,
     const int tid = threadIdx.x;
     const int z1c = pairs[id * 6], y1c = pairs[id * 6 + 1], x1c = pairs[id * 6 + 2];
     const int z2c = pairs[id * 6 + 3], y2c = pairs[id * 6 + 4], x2c = pairs[id * 6 + 5];
-    const uint32_t rnd0 = (uint32_t)z1c * (uint32_t)z2c * (uint32_t)y1c * (uint32_t)y2c *
-                          (uint32_t)x1c * (uint32_t)x2c;
+    // pair_org: origin the reference's coordinates of this pair are relative to (its seed is
+    // the product of the coordinates it was handed, computePatchGraph.cu:24-27)
+    const int oz_ = pair_org ? pair_org[id * 3] : 0, oy_ = pair_org ? pair_org[id * 3 + 1] : 0,
+              ox_ = pair_org ? pair_org[id * 3 + 2] : 0;
+    const uint32_t rnd0 = (uint32_t)(z1c - oz_) * (uint32_t)(z2c - oz_) * (uint32_t)(y1c - oy_) *
+                          (uint32_t)(y2c - oy_) * (uint32_t)(x1c - ox_) * (uint32_t)(x2c - ox_);
     // patches further apart than 2*ps on an axis share no slot: every term is skipped
     // by the offset test (:98-101), sum and count stay 0
     if (abs(z2c - z1c) > 2 * g.psz || abs(y2c - y1c) > 2 * g.psy || abs(x2c - x1c) > 2 * g.psx) {
@@ -393,7 +400,8 @@ extern "C" int64_t ppp_patch_graph_scratch_bytes(const ppp_cfg* cfg, int64_t n)
 template <class Src>
 static int patch_graph_launch(Src src, const uint8_t* flags, const int32_t* fgidx,
                               const float* cons, const uint32_t* pairs, int64_t n,
-                              const ppp_cfg* cfg, float* aff, void* scratch, void* stream)
+                              const ppp_cfg* cfg, float* aff, void* scratch, void* stream,
+                              const int32_t* pair_org = nullptr)
 {
     if (n <= 0) return 0;
     Geo g = make_geo(*cfg);
@@ -403,14 +411,14 @@ static int patch_graph_launch(Src src, const uint8_t* flags, const int32_t* fgid
             return ppp_fail(-1, "ppp_patch_graph: patch axis larger than 128");
         // rnd0 = z*z2*y*y2*x*x2 (computePatchGraph.cu:24-27) is 0 for every pair of a
         // single-slice volume: no sub-sampling, no factor tables
-        const bool lcg = g.Z > 1;
+        const bool lcg = g.Z > 1 || pair_org != nullptr;
         if (scratch == nullptr) return ppp_fail(-1, "ppp_patch_graph: scratch required");
         if (lcg)
             patch_graph_ref_kernel<true, Src><<<(unsigned)n, PGR_THREADS, 0, (cudaStream_t)stream>>>(
-                src, flags, fgidx, cons, pairs, *cfg, aff, (int32_t*)scratch);
+                src, flags, fgidx, cons, pairs, *cfg, aff, (int32_t*)scratch, pair_org);
         else
             patch_graph_ref_kernel<false, Src><<<(unsigned)n, PGR_THREADS, 0, (cudaStream_t)stream>>>(
-                src, flags, fgidx, cons, pairs, *cfg, aff, (int32_t*)scratch);
+                src, flags, fgidx, cons, pairs, *cfg, aff, (int32_t*)scratch, pair_org);
         return ppp_check("ppp_patch_graph(reference order)");
     }
     size_t smem = (size_t)g.P * 12 + 16;
@@ -421,7 +429,7 @@ static int patch_graph_launch(Src src, const uint8_t* flags, const int32_t* fgid
         if (e != cudaSuccess) return ppp_fail((int)e, "ppp_patch_graph: smem attribute");
     }
     patch_graph_kernel<Src><<<(unsigned)n, PG_THREADS, smem, (cudaStream_t)stream>>>(
-        src, flags, fgidx, cons, pairs, *cfg, aff);
+        src, flags, fgidx, cons, pairs, *cfg, aff, pair_org);
     return ppp_check("ppp_patch_graph");
 }
 
@@ -437,12 +445,13 @@ extern "C" int ppp_patch_graph(const float* pred, const uint8_t* flags,
 
 extern "C" int ppp_patch_graph_rows(const uint16_t* patches, const int32_t* vox2row,
                                     const uint8_t* flags, const int32_t* fgidx,
-                                    const float* cons, const uint32_t* pairs, int64_t n,
+                                    const float* cons, const uint32_t* pairs,
+                                    const int32_t* pair_org, int64_t n,
                                     const ppp_cfg* cfg, float* aff, void* scratch, void* stream)
 {
     Geo g = make_geo(*cfg);
     return patch_graph_launch(SrcRows{(const __half*)patches, vox2row, g.P}, flags, fgidx, cons,
-                              pairs, n, cfg, aff, scratch, stream);
+                              pairs, n, cfg, aff, scratch, stream, pair_org);
 }
 
 // ---------------------------------------------------------------------------

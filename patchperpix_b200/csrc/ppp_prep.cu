@@ -395,7 +395,8 @@ extern "C" int ppp_prepare_rows(const uint16_t* patches, const int32_t* vox2row,
 template <class Src>
 __global__ void __launch_bounds__(256)
 received_values_kernel(Src src, const uint8_t* __restrict__ flags,
-                       const int32_t* __restrict__ rowvox, int64_t F, ppp_cfg cfg,
+                       const int32_t* __restrict__ rowvox, const uint8_t* __restrict__ need,
+                       int64_t F, ppp_cfg cfg,
                        float* __restrict__ rv, uint16_t* __restrict__ rb16, int rbw)
 {
     Geo g = make_geo(cfg);
@@ -403,6 +404,7 @@ received_values_kernel(Src src, const uint8_t* __restrict__ flags,
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t row = (int64_t)blockIdx.x * 8 + w;
     if (row >= F) return;
+    if (need != nullptr && !need[row]) return;
     const int nrw = g.psz * g.psy;
     const int v = rowvox[row];
     for (int i = lane; i < 64; i += 32) s_bits[w][i] = 0u;
@@ -442,33 +444,35 @@ static int received_check(const Geo& g, int64_t F)
     return 0;
 }
 
-extern "C" int32_t ppp_received_row_words(const ppp_cfg* cfg)
+extern "C" int64_t ppp_received_row_words(const ppp_cfg* cfg)
 {
     Geo g = make_geo(*cfg);
     return ((g.psz * g.psy + 7) / 8) * 8;
 }
 
 extern "C" int ppp_received(const float* pred, const uint8_t* flags, const int32_t* rowvox,
-                            int64_t F, const ppp_cfg* cfg, float* rv, uint16_t* rb16,
-                            void* stream)
+                            const uint8_t* need, int64_t F, const ppp_cfg* cfg, float* rv,
+                            uint16_t* rb16, void* stream)
 {
     if (F <= 0) return 0;
     Geo g = make_geo(*cfg);
     if (int rc = received_check(g, F)) return rc;
     received_values_kernel<SrcDense><<<(unsigned)((F + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-        SrcDense{pred, g.V}, flags, rowvox, F, *cfg, rv, rb16, ppp_received_row_words(cfg));
+        SrcDense{pred, g.V}, flags, rowvox, need, F, *cfg, rv, rb16,
+        (int)ppp_received_row_words(cfg));
     return ppp_check("ppp_received");
 }
 
 extern "C" int ppp_received_rows(const uint16_t* patches, const int32_t* vox2row,
-                                 const uint8_t* flags, const int32_t* rowvox, int64_t F,
+                                 const uint8_t* flags, const int32_t* rowvox,
+                                 const uint8_t* need, int64_t F,
                                  const ppp_cfg* cfg, float* rv, uint16_t* rb16, void* stream)
 {
     if (F <= 0) return 0;
     Geo g = make_geo(*cfg);
     if (int rc = received_check(g, F)) return rc;
     received_values_kernel<SrcRows><<<(unsigned)((F + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-        SrcRows{(const __half*)patches, vox2row, g.P}, flags, rowvox, F, *cfg, rv, rb16,
-        ppp_received_row_words(cfg));
+        SrcRows{(const __half*)patches, vox2row, g.P}, flags, rowvox, need, F, *cfg, rv, rb16,
+        (int)ppp_received_row_words(cfg));
     return ppp_check("ppp_received_rows");
 }

@@ -128,13 +128,13 @@ _SIGS = {
     'ppp_paint': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
     'ppp_paint_channels': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
     'ppp_paint_patches': (ctypes.c_int, ['p', 'p', 'i64', 'p', 'cfg', 'p', 'p']),
-    'ppp_received_row_words': (ctypes.c_int32, ['cfg']),
-    'ppp_received': (ctypes.c_int, ['p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
-    'ppp_received_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
+    'ppp_received_row_words': (ctypes.c_int64, ['cfg']),
+    'ppp_received': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
+    'ppp_received_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
     'ppp_consensus_small': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
     'ppp_gate_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'cfg', 'p', 'p']),
     'ppp_prepare_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p', 'p', 'p']),
-    'ppp_patch_graph_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
+    'ppp_patch_graph_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
     'ppp_paint_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p']),
     'ppp_decode_scratch_bytes': (ctypes.c_int64, ['i64']),
     'ppp_decode': (ctypes.c_int, ['p', 'i64'] + ['p'] * 14 + ['i32', 'p', 'p', 'p']),
@@ -167,6 +167,11 @@ def load_library():
 
 class PppError(RuntimeError):
     pass
+
+
+# set by a profiler (bench.py) to a callable(name, value): lets a stage report how many
+# units a launch really processes when that is only known on the device
+profile_hook = None
 
 
 def ptr(t):

@@ -41,8 +41,10 @@ from .stitch_patch_graph import (get_offsets, face_candidates, face_pairs, _dist
 logger = logging.getLogger(__name__)
 
 
-def slab_partition(shape, chunksize, world, axis=None):
+def slab_partition(shape, chunksize, world, axis=None, weights=None):
     """block rows along `axis` dealt to the ranks in contiguous runs.
+    weights: cost of every block row along `axis` (e.g. its foreground count); the
+    runs then minimise the largest per-rank cost, else they hold equal row counts.
     Returns (axis, [(lo, hi)] * world) in voxels; empty slabs have lo == hi."""
     shape = [int(s) for s in shape]
     chunk = [int(min(c, s)) for c, s in zip(chunksize, shape)]
@@ -50,9 +52,29 @@ def slab_partition(shape, chunksize, world, axis=None):
     if axis is None:
         axis = int(np.argmax(nrows))
     n = nrows[axis]
+    if weights is None:
+        cuts = [(r * n) // world for r in range(world + 1)]
+    else:
+        w = np.asarray(weights, np.float64)
+        assert len(w) == n, "one weight per block row"
+        pre = np.concatenate([[0.0], np.cumsum(w)])
+        # best[k][i] = smallest possible largest run when rows [0, i) go to k ranks
+        best = np.full((world + 1, n + 1), np.inf)
+        arg = np.zeros((world + 1, n + 1), np.int64)
+        best[0][0] = 0.0
+        for k in range(1, world + 1):
+            for i in range(n + 1):
+                for j in range(i + 1):
+                    c = max(best[k - 1][j], pre[i] - pre[j])
+                    if c < best[k][i]:
+                        best[k][i], arg[k][i] = c, j
+        cuts = [n]
+        for k in range(world, 0, -1):
+            cuts.append(int(arg[k][cuts[-1]]))
+        cuts = cuts[::-1]
     out = []
     for r in range(world):
-        a, b = (r * n) // world, ((r + 1) * n) // world
+        a, b = cuts[r], cuts[r + 1]
         out.append((min(a * chunk[axis], shape[axis]), min(b * chunk[axis], shape[axis])))
     return axis, out
 
@@ -236,6 +258,68 @@ def _face_job(shard, candidates, pa, ps, kwargs, block_fn=None):
     return overlapping.astype(np.uint32), np.asarray(aff, np.float32)
 
 
+def _face_batch(shard, faces, ps, kwargs):
+    """the face jobs `faces` = [(job, (candidates, pair index array))] as ONE pass over
+    the bounding box of their regions.  Returns {job: (pairs u32 [n,6] volume coordinates,
+    aff f32 [n])}, identical to running _face_job on each of them."""
+    import torch
+    from .assembly import BlockAssembler
+    margin = ps // 2
+    shape = np.asarray(shard.shape)
+    per = []
+    for j, (candidates, pa) in faces:
+        cleaned = candidates[np.unique(pa.reshape(-1))]
+        bb_start = np.maximum(np.min(cleaned, axis=0) - ps, 0)
+        bb_stop = np.minimum(np.max(cleaned, axis=0) + ps, shape)
+        r_start = np.maximum(bb_start - margin, 0)                    # load_region clips
+        r_stop = np.minimum(np.maximum(bb_stop, bb_start + 1) + margin, shape)
+        origin = r_start if kwargs.get('ppp_fix_face_origin', False) else bb_start - margin
+        overlapping = np.concatenate([candidates[pa[:, 0]], candidates[pa[:, 1]]], axis=1)
+        rel_p = overlapping - np.tile(origin, 2)
+        inside = np.all((rel_p >= 0) & (rel_p < np.tile(r_stop - r_start, 2)), axis=1)
+        eff_p = rel_p + np.tile(r_start, 2)          # where the kernel really looks (:317-321)
+        eff_c = cleaned - origin + r_start
+        per.append((j, overlapping, inside, eff_p, eff_c, r_start, r_stop))
+    b_start = np.min([p[5] for p in per], axis=0)
+    b_stop = np.max([p[6] for p in per], axis=0)
+    src, fg, mask, numinst, _ = shard.region(b_start, b_stop, **kwargs)
+    bshape = tuple(int(v) for v in (b_stop - b_start))
+    ckw = {k: v for k, v in kwargs.items() if k != 'patchshape'}
+    asm = BlockAssembler(src, fg, (numinst > 1).to(torch.uint8), ps, **ckw)
+    asm.prepare(want_dp=False, want_rv=False, want_masks=False)
+    dev = shard.dev
+    pk = np.concatenate([p[3][p[2]] for p in per]) - np.tile(b_start, 2)
+    org = np.concatenate([np.broadcast_to(p[5] - b_start, (int(p[2].sum()), 3)) for p in per])
+    cen = np.concatenate([p[4] for p in per]) - b_start
+    ok = np.all((cen >= 0) & (cen < np.asarray(bshape)), axis=1)
+    cen = torch.from_numpy(cen[ok]).to(dev)
+    seed = torch.zeros((1, 1) + bshape, dtype=torch.float32, device=dev)
+    seed[0, 0, cen[:, 0], cen[:, 1], cen[:, 2]] = 1.0
+    win = torch.nn.functional.max_pool3d(seed, kernel_size=tuple(int(p) for p in ps), stride=1,
+                                         padding=tuple(int(r) for r in margin))
+    rv_l = asm.rowvox.long()
+    need = win.reshape(-1)[rv_l].to(torch.uint8).contiguous()
+    # their partners (anything within 2*ps-1) must have tables too
+    win2 = torch.nn.functional.max_pool3d(win, kernel_size=tuple(int(2 * p - 1) for p in ps),
+                                          stride=1, padding=tuple(int(p - 1) for p in ps))
+    asm.received(win2.reshape(-1)[rv_l].to(torch.uint8).contiguous())
+    asm.consensus(need=need)
+    aff_all = np.zeros(0, np.float32)
+    if len(pk):
+        pairs_dev = torch.from_numpy(np.ascontiguousarray(pk.astype(np.uint32)).view(np.int32)).to(dev)
+        org_dev = torch.from_numpy(np.ascontiguousarray(org.astype(np.int32))).to(dev)
+        aff_all = asm.patch_graph(pairs_dev, pair_org=org_dev).cpu().numpy()
+    out = {}
+    o = 0
+    for j, overlapping, inside, _, _, _, _ in per:
+        n = int(inside.sum())
+        aff = np.zeros(len(overlapping), np.float32)
+        aff[inside] = aff_all[o:o + n]
+        o += n
+        out[j] = (overlapping.astype(np.uint32), aff)
+    return out
+
+
 def _run_jobs(jobs, fn, workers):
     """run fn(job) for every job; with workers > 1 from that many host threads, each
     on its own CUDA stream, so that the host part of one job (pair search, sizes
@@ -387,7 +471,7 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
     chunksize = np.minimum(np.asarray(kwargs['chunksize']), shape)
     kwargs = dict(kwargs, chunksize=chunksize)
     if workers is None:
-        workers = int(kwargs.get('ppp_block_workers', 3))
+        workers = int(kwargs.get('ppp_block_workers', 6))
     offsets = get_offsets(shape, chunksize)
     nblk = len(offsets)
 
@@ -439,19 +523,19 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
                 continue
             jobs.append((b, nb, dim))
 
-    sel_lock = threading.Lock()
-
     def selected_of(b):
-        """the selected patches of a block = the nodes of its pair list (:166-171)"""
-        with sel_lock:
-            if b not in selected:
-                p = blocks[b][0].reshape(-1, 3).astype(np.int64)
-                key = (p[:, 0] * shape[1] + p[:, 1]) * shape[2] + p[:, 2]
-                _, first = np.unique(key, return_index=True)     # sorted by (z,y,x) like
-                selected[b] = p[first]                           # np.unique(axis=0)
-            return selected[b]
+        """the selected patches of a block = the nodes of its pair list (:166-171);
+        computed where first needed, from any thread (a race only repeats the work)"""
+        got = selected.get(b)
+        if got is None:
+            p = blocks[b][0].reshape(-1, 3).astype(np.int64)
+            key = (p[:, 0] * shape[1] + p[:, 1]) * shape[2] + p[:, 2]
+            _, first = np.unique(key, return_index=True)     # sorted by (z,y,x) like
+            got = selected[b] = p[first]                     # np.unique(axis=0)
+        return got
 
-    def face(j):
+    def face_host(j):
+        """candidates and cross pairs of face job j (host: KD tree, set order)"""
         b, nb, dim = jobs[j]
         cur, nbc = face_candidates(selected_of(b), selected_of(nb), offsets[b], dim, ps)
         if len(cur) == 0 or len(nbc) == 0:
@@ -459,9 +543,32 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
         cands, pa = face_pairs(cur, nbc, ps)
         if len(pa) == 0:
             return None
-        return _face_job(shard, cands, pa, ps, kwargs, block_fn)
+        return cands, pa
+
+    def face(j):
+        cp = face_host(j)
+        if cp is None:
+            return None
+        return _face_job(shard, cp[0], cp[1], ps, kwargs, block_fn)
     my_jobs = [j for j in range(len(jobs)) if owner[jobs[j][0]] == rank]
-    res = _run_jobs(my_jobs, face, workers)
+    if block_fn is not None or not kwargs.get('ppp_batch_faces', True):
+        res = _run_jobs(my_jobs, face, workers)
+    else:
+        # all face jobs of one block row share ONE region: the consensus of the slots a
+        # face job reads does not depend on the extent of its region (every centre that can
+        # vote on them lies inside: the region is padded by patchshape + patchshape//2,
+        # :261-278), so one gate/prepare/consensus/patch-graph pass over the row serves them all
+        host = _run_jobs(my_jobs, face_host, workers)
+        lap('faces_host')
+        groups = {}
+        for j, cp in zip(my_jobs, host):
+            if cp is not None:
+                groups.setdefault(int(offsets[jobs[j][0]][axis]), []).append((j, cp))
+        got = {}
+        for part in _run_jobs(sorted(groups), lambda k: _face_batch(shard, groups[k], ps, kwargs),
+                              min(workers, 2)):
+            got.update(part)
+        res = [got.get(j) for j in my_jobs]
     my_faces = {j: r for j, r in zip(my_jobs, res) if r is not None}
     lap('faces')
     faces = _allgather_edges(my_faces, len(jobs), lambda j: owner[jobs[j][0]])  # exchange (2)
@@ -471,16 +578,14 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
     plist, alist = [], []
     jidx = {}
     for j, (b, nb, dim) in enumerate(jobs):
-        jidx.setdefault(b, []).append(j)
-    for b in range(nblk):
-        if b not in blocks:
-            continue
+        if j in faces:
+            jidx.setdefault(b, []).append(j)
+    for b in sorted(blocks):
         plist.append(blocks[b][0])
         alist.append(blocks[b][1])
-        for j in jidx.get(b, []):
-            if j in faces:
-                plist.append(faces[j][0])
-                alist.append(faces[j][1])
+        for j in jidx.get(b, ()):
+            plist.append(faces[j][0])
+            alist.append(faces[j][1])
     info = dict(n_blocks=nblk, n_faces=len(jobs), n_edges=int(sum(len(a) for a in alist)),
                 my_blocks=len(my_blocks), my_faces=len(my_jobs), halo_bytes=shard.halo_bytes,
                 phase_ms=tm,

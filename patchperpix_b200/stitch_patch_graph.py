@@ -73,6 +73,12 @@ class VolumeInputs:
     """
 
     def __init__(self, pred, numinst_prob=None, fg=None):
+        if len(pred.shape) == 3:                 # 2-D prediction [P,Y,X]: lifted to Z = 1
+            pred = pred[:, None]                 # (stitch_patch_graph.py:766-767)
+            if numinst_prob is not None and len(numinst_prob.shape) == 3:
+                numinst_prob = numinst_prob[:, None]
+            if fg is not None and len(fg.shape) == 2:
+                fg = fg[None]
         self.pred = pred
         self.numinst_prob = numinst_prob
         self.fg = fg
@@ -97,24 +103,24 @@ class VolumeInputs:
         return True
 
     def _fg_numinst(self, start, stop, **kwargs):
-        """foreground / numinst of a region, precedence as in the reference's
-        returnFg (utilVoteInstances.py:306-322) and stitch_patch_graph.py:610-637."""
-        from .utilVoteInstances import getFgThreshold
-        th = getFgThreshold(**kwargs)
-        numinst = None
+        """foreground / numinst of a region: fg_key if set, else numinst > 0, else
+        the centre channel (returnFg, utilVoteInstances.py:306-322); numinst from
+        numinst_key whenever it is set (stitch_patch_graph.py:610-637)."""
+        from .utilVoteInstances import resolve_foreground
+        numinst = fg = mid = None
         if kwargs.get("numinst_key") is not None and self.numinst_prob is not None:
             prob, _ = load_region(self.numinst_prob, start, stop)
             numinst = numinst_from_prob(np.asarray(prob), **kwargs)
-            foreground = (numinst > 0) > th
-        elif kwargs.get("fg_key") is not None and self.fg is not None:
+        if kwargs.get("fg_key") is not None and self.fg is not None:
             fg, _ = load_region(self.fg, start, stop)
-            foreground = np.squeeze(np.asarray(fg)) > th
-            if foreground.ndim == 2:
-                foreground = foreground[None]
-        else:
-            mid = int(np.prod(kwargs['patchshape'])) // 2
-            m, _ = load_region(self.pred[mid:mid + 1], start, stop)
-            foreground = np.asarray(m)[0] > th
+            fg = np.asarray(fg)
+        elif numinst is None:
+            m = int(np.prod(kwargs['patchshape'])) // 2
+            mid, _ = load_region(self.pred[m:m + 1], start, stop)
+            mid = np.asarray(mid)[0]
+        foreground = resolve_foreground(fg=fg, numinst=numinst, mid=mid, **kwargs)
+        if foreground.ndim == 2:
+            foreground = foreground[None]
         if numinst is None:
             numinst = np.copy(foreground)
         return foreground, numinst
@@ -242,17 +248,48 @@ def stitch_arrays(inputs, block_fn=default_block_fn, paint_fn=None, **kwargs):
     world = dist.get_world_size() if dist else 1
     ps = np.asarray(kwargs['patchshape'])
     shape = inputs.shape
-    chunksize = np.minimum(np.asarray(kwargs['chunksize']), shape)
+    # only_bb (stitch_patch_graph.py:745-764, 137-138): the block grid covers the
+    # bounding box of the foreground and starts at its corner
+    bb_offset = np.asarray(kwargs.pop('bb_offset', np.zeros(3, int)), dtype=int)
+    bb_shape = np.asarray(kwargs.pop('bb_shape', shape), dtype=int)
+    chunksize = np.minimum(np.asarray(kwargs['chunksize']), bb_shape)
     kwargs = dict(kwargs, chunksize=chunksize)
-    offsets = get_offsets(shape, chunksize)
+    offsets = [o + bb_offset for o in get_offsets(bb_shape, chunksize)]
     nblk = len(offsets)
     if block_fn is default_block_fn and kwargs.get('ppp_device_volume', True):
         inputs.to_device()               # whole volume in HBM when it fits
 
+    # block cache (stitch_patch_graph.py:584-587, 649-669): results of earlier runs are
+    # kept under volumes/blocks/<z_y_x>/{patch_pairs, aff_graph_mat} (pairs relative to
+    # the block offset) and, per face, under <block>/<neighbour>/ (volume coordinates)
+    cache = kwargs.pop('block_cache', None)
+    tmp_key = 'volumes/blocks'
+
+    def cached(key):
+        if cache is not None and key + '/patch_pairs' in cache:
+            return (np.array(cache[key + '/patch_pairs']).astype(np.uint32).reshape(-1, 6),
+                    np.array(cache[key + '/aff_graph_mat']).astype(np.float32))
+        return None
+
+    def store(key, pairs, aff):
+        if cache is not None and pairs is not None:
+            cache.create_dataset(key + '/patch_pairs', data=np.asarray(pairs, np.uint32),
+                                 overwrite=True)
+            cache.create_dataset(key + '/aff_graph_mat', data=np.asarray(aff, np.float32),
+                                 overwrite=True)
+
     # ---- phase 1: blocks, round-robin over the ranks (offsets.py:45) -----------
     mine = {}
     for b in range(rank, nblk, world):
+        key = tmp_key + '/' + get_offset_str(offsets[b])
+        got = cached(key)
+        if got is not None:
+            mine[b] = ((got[0].astype(np.int64) + np.tile(offsets[b], 2)).astype(np.uint32),
+                       got[1])
+            continue
         mine[b] = assemble_block(inputs, offsets[b], block_fn, **kwargs)
+        if mine[b][0] is not None:
+            store(key, mine[b][0].astype(np.int64) - np.tile(offsets[b], 2), mine[b][1])
     # exchange (1): per-block pairs (selected patches are derived from them)
     blocks = {}
     for part in _allgather_obj(mine):
@@ -280,6 +317,11 @@ def stitch_arrays(inputs, block_fn=default_block_fn, paint_fn=None, **kwargs):
     my_faces = {}
     for j in range(rank, len(jobs), world):
         b, nb, dim = jobs[j]
+        fkey = tmp_key + '/' + get_offset_str(offsets[b]) + '/' + get_offset_str(offsets[nb])
+        got = cached(fkey)
+        if got is not None:
+            my_faces[j] = got
+            continue
         cur, nbc = face_candidates(selected[b], selected[nb], offsets[b], dim, ps)
         if len(cur) == 0 or len(nbc) == 0:
             continue
@@ -287,6 +329,7 @@ def stitch_arrays(inputs, block_fn=default_block_fn, paint_fn=None, **kwargs):
         if len(pa) == 0:
             continue
         my_faces[j] = assemble_face(inputs, cands, pa, block_fn, **kwargs)
+        store(fkey, *my_faces[j])
     faces = {}
     for part in _allgather_obj(my_faces):                        # exchange (2)
         faces.update(part)
@@ -373,31 +416,83 @@ def paint_global(inputs, pairs, aff, rank=0, world=1, **kwargs):
     return inst.cpu().numpy().astype(np.uint32)
 
 
+def bounding_box(inputs, **kwargs):
+    """(bb_offset, bb_shape) of stitch_patch_graph.py:745-771; None: no foreground."""
+    from .postprocess import foreground_bbox
+    if not kwargs.get('only_bb'):
+        return np.zeros(3, int), np.asarray(inputs.shape)
+    return foreground_bbox(inputs.foreground(**kwargs), **kwargs)
+
+
+def finish_outputs(instances, foreground, **kwargs):
+    """stitch_patch_graph.py:824-894 on the device: optional removal of small
+    instances + relabelling, the masked volume, optional dilated volumes.
+    instances: int tensor / array [Z,Y,X]; returns {dataset name: uint16 numpy}."""
+    import torch
+    from . import postprocess as pp
+    res_key = kwargs.get('res_key', 'vote_instances')
+    dev = torch.device('cuda') if torch.cuda.is_available() else torch.device('cpu')
+    inst = torch.as_tensor(np.asarray(instances).astype(np.int64)
+                           if not torch.is_tensor(instances) else instances).to(dev)
+    fg = torch.as_tensor(np.squeeze(np.asarray(foreground)) != 0).to(dev)
+    if fg.dim() == 2:
+        fg = fg[None]
+    if kwargs.get('remove_small_comps', 0) > 0:
+        inst = pp.relabel(pp.remove_small_components(inst, kwargs['remove_small_comps']))
+
+    def u16(t):
+        return t.cpu().numpy().astype(np.uint16)
+    out = {res_key: u16(inst), 'vote_foreground': u16(fg),
+           'vote_instances_masked': u16(torch.where(fg, inst, torch.zeros_like(inst)))}
+    if kwargs.get('dilate_instances', False):
+        dil = pp.dilate_instances(inst)
+        out[res_key + '_dil_1'] = u16(dil)
+        out[res_key + '_masked_dil_1'] = u16(torch.where(fg, dil, torch.zeros_like(dil)))
+    return out
+
+
 def main(pred_file, result_folder='.', **kwargs):
     """stitch_patch_graph.py:672-896: file-level entry point (zarr in,
-    `<sample>.hdf` / `.npz` out)."""
-    from .io_util import open_zarr, write_result
+    `<sample>.hdf` / `.npz` out).  Under torch.distributed every rank works, rank 0
+    writes."""
+    from .io_util import open_container, write_result
+    if kwargs.get('graphToInst', False) or kwargs.get('blockwise_old_stitch_fn', False):
+        raise NotImplementedError("stitch_patch_graph options graphToInst / "
+                                  "blockwise_old_stitch_fn are outside the B200 hot path")
     assert os.path.exists(pred_file), \
         'Prediction file {} does not exist. Please check!'.format(pred_file)
     sample = os.path.basename(pred_file).split('.')[0]
     kwargs['result_folder'] = result_folder
-    in_f = open_zarr(pred_file, 'r')
-    aff_key = kwargs['aff_key']
-    pred = in_f[aff_key]
+    in_f = open_container(pred_file, 'r')
+    pred = in_f[kwargs['aff_key']]
     numinst_prob = in_f[kwargs['numinst_key']] if kwargs.get('numinst_key') else None
-    fg = in_f[kwargs['fg_key']] if (numinst_prob is None and kwargs.get('fg_key')) else None
-    if kwargs.get('only_bb'):
-        raise NotImplementedError("only_bb (bounding-box crop with skeletonisation, "
-                                  "stitch_patch_graph.py:745-764) is outside the hot path")
+    fg = in_f[kwargs['fg_key']] if kwargs.get('fg_key') else None
+    if numinst_prob is not None:
+        assert tuple(pred.shape[1:]) == tuple(numinst_prob.shape[1:]), \
+            'Please check: affinity and numinst shape do not match!'
     inputs = VolumeInputs(pred, numinst_prob, fg)
-    instances, foreground, _ = stitch_arrays(inputs, **kwargs)
-    res_key = kwargs.get('res_key', 'vote_instances')
-    os.makedirs(result_folder, exist_ok=True)
-    fg16 = np.squeeze(foreground).astype(np.uint16)
-    masked = instances.copy()
-    masked[fg16 == 0] = 0
-    write_result(os.path.join(result_folder, sample),
-                 {res_key: instances.astype(np.uint16), 'vote_foreground': fg16,
-                  'vote_instances_masked': masked.astype(np.uint16)},
-                 kwargs.get('output_format', 'hdf'))
+    bb = bounding_box(inputs, **kwargs)
+    if bb is None:
+        logger.info('Volume has no foreground voxel, returning...')
+        return
+    dist = _dist()
+    cache = None
+    if kwargs.get('ppp_block_cache', True) and (dist is None or dist.get_world_size() == 1):
+        from .io_util import open_zarr
+        cache = open_zarr(os.path.join(result_folder, sample + '.zarr'), 'a')
+    instances, foreground, _ = stitch_arrays(inputs, bb_offset=bb[0], bb_shape=bb[1],
+                                             block_cache=cache, **kwargs)
+    if dist is None or dist.get_rank() == 0:
+        os.makedirs(result_folder, exist_ok=True)
+        out = finish_outputs(instances, foreground, **kwargs)
+        if kwargs.get('save_mip', False):                        # :815-821, 840-845
+            from .postprocess import color, write_png
+            res = out[kwargs.get('res_key', 'vote_instances')]
+            write_png(os.path.join(result_folder, sample + (
+                '_cleaned.png' if kwargs.get('remove_small_comps', 0) > 0 else '.png')),
+                color(np.max(res, axis=0)))
+        write_result(os.path.join(result_folder, sample), out,
+                     kwargs.get('output_format', 'hdf'))
+    if dist is not None:
+        dist.barrier()
     return instances

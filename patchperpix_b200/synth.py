@@ -171,7 +171,7 @@ def neurites_3d(shape=(256, 1024, 1024), n=300, seed=4, radius=(2, 3),
 
 
 def neurite_rows(shape, patchshape, axis=0, lo=0, hi=None, seed=4, noise=0.04, device='cuda',
-                 chunk_rows=1 << 17, box=None, **kw):
+                 chunk_rows=1 << 17, box=None, volume=None, **kw):
     """the compact row form of make_case('neurites', ...) for the slab
     lo <= coord[axis] < hi: (coords i32 [G,3] global, patches f16 [G,P], numinst u8 [G])
     as torch tensors on `device`, rows in raster order.  Values are bit-identical to
@@ -183,7 +183,12 @@ def neurite_rows(shape, patchshape, axis=0, lo=0, hi=None, seed=4, noise=0.04, d
     shape = tuple(int(s) for s in shape)
     hi = shape[axis] if hi is None else hi
     wlo, whi = max(lo - r[axis], 0), min(hi + r[axis], shape[axis])
-    labels, numinst = neurites_3d(shape, seed=seed, window=(axis, wlo, whi), **kw)
+    if volume is not None:           # (labels, numinst) of the WHOLE volume, already drawn
+        wsl = [slice(None)] * 3
+        wsl[axis] = slice(wlo, whi)
+        labels, numinst = volume[0][tuple(wsl)], volume[1][tuple(wsl)]
+    else:
+        labels, numinst = neurites_3d(shape, seed=seed, window=(axis, wlo, whi), **kw)
     dev = torch.device(device)
     lab_t = torch.as_tensor(labels, device=dev)
     ni_t = torch.as_tensor(numinst, device=dev)

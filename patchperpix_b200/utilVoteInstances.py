@@ -42,44 +42,41 @@ def maybeLoadNuminst(f, **kwargs):
     return None
 
 
-def loadFg(f, **kwargs):
-    """utilVoteInstances.py:275-303: (foreground bool, key)."""
-    aff_key = kwargs['aff_key']
-    fg_key = kwargs.get('fg_key', None)
-    numinst_key = kwargs.get('numinst_key', None)
-    fg_thresh = getFgThreshold(**kwargs)
-    if fg_key is not None:
-        foreground = np.array(f[fg_key])
-        key = fg_key
-    elif numinst_key is not None:
-        numinst_prob = np.array(f[numinst_key])
-        numinst = np.argmax(numinst_prob, axis=0).astype(np.uint8)
-        if kwargs.get('numinst_threshs'):
-            numinst = np.zeros(numinst_prob.shape[1:], dtype=np.uint8)
-            for i in range(len(kwargs['numinst_threshs'])):
-                numinst[numinst_prob[i + 1] > kwargs['numinst_threshs'][i]] = i + 1
-        foreground = np.expand_dims((numinst > 0).astype(np.float32), axis=0)
-        key = numinst_key
+def resolve_foreground(fg=None, numinst=None, mid=None, **kwargs):
+    """the one foreground rule of the stage (utilVoteInstances.py:275-322): the
+    `fg_key` array if that key is set, else `numinst > 0` if `numinst_key` is set,
+    else the centre channel of the prediction; thresholded with `fg_thresh_vi` if
+    positive, else `patch_threshold`.  Arrays are squeezed to the volume's own
+    dimensions (the reference's file loader keeps a leading 1 in two of the three
+    branches, which breaks its own 3-D non-blockwise path)."""
+    if kwargs.get('fg_key') is not None and fg is not None:
+        src = np.squeeze(np.asarray(fg))
+    elif kwargs.get('numinst_key') is not None and numinst is not None:
+        src = np.squeeze(np.asarray(numinst)) > 0
     else:
-        mid = np.prod(kwargs['patchshape']) // 2
-        foreground = np.expand_dims(np.array(f[aff_key][mid]), axis=0)
-        key = aff_key
-    return foreground > fg_thresh, key
+        assert mid is not None, "no foreground source"
+        src = np.squeeze(np.asarray(mid))
+    return src > getFgThreshold(**kwargs)
+
+
+def loadFg(f, **kwargs):
+    """utilVoteInstances.py:275-303 on an open container: (foreground bool, key)."""
+    fg_key, numinst_key = kwargs.get('fg_key'), kwargs.get('numinst_key')
+    if fg_key is not None:
+        return resolve_foreground(fg=np.array(f[fg_key]), **kwargs), fg_key
+    if numinst_key is not None:
+        return resolve_foreground(numinst=maybeLoadNuminst(f, **kwargs), **kwargs), numinst_key
+    mid = int(np.prod(kwargs['patchshape'])) // 2
+    return resolve_foreground(mid=np.array(f[kwargs['aff_key']][mid]), **kwargs), \
+        kwargs['aff_key']
 
 
 def returnFg(affs, numinst, fg, **kwargs):
-    """utilVoteInstances.py:306-322."""
-    fg_key = kwargs.get('fg_key', None)
-    numinst_key = kwargs.get('numinst_key', None)
-    fg_thresh = getFgThreshold(**kwargs)
-    if fg_key is not None:
-        foreground = np.squeeze(fg)
-    elif numinst_key is not None:
-        foreground = numinst > 0
-    else:
-        mid = np.prod(kwargs['patchshape']) // 2
-        foreground = affs[mid]
-    return foreground > fg_thresh
+    """utilVoteInstances.py:306-322 on the arrays of one block."""
+    mid = None
+    if kwargs.get('fg_key') is None and kwargs.get('numinst_key') is None:
+        mid = affs[int(np.prod(kwargs['patchshape'])) // 2]
+    return resolve_foreground(fg=fg, numinst=numinst, mid=mid, **kwargs)
 
 
 def getResKey(**kwargs):
@@ -94,16 +91,8 @@ def getResKey(**kwargs):
 
 
 def _open(aff_file):
-    if aff_file.endswith(".hdf"):
-        try:
-            import h5py
-        except ImportError as e:
-            raise RuntimeError("reading %s needs h5py" % aff_file) from e
-        return h5py.File(aff_file, 'r')
-    if aff_file.endswith(".zarr"):
-        from .io_util import open_zarr
-        return open_zarr(aff_file)
-    raise RuntimeError("unsupported container " + aff_file)
+    from .io_util import open_container
+    return open_container(aff_file, 'r')
 
 
 def loadAffinities(aff_file, res_ext, patchshape=None, **kwargs):

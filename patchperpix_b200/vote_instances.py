@@ -93,6 +93,10 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
         if kwargs.get(k, False):
             raise NotImplementedError("vote_instances option %r is outside "
                                       "the B200 hot path" % k)
+    if float(kwargs.get('sample', 1.0)) < 1.0:
+        raise NotImplementedError("vote_instances option 'sample' < 1.0 (random sub-sampling of "
+                                  "the patch sets, get_patch_sets.py:52) is outside the B200 hot "
+                                  "path")
     patchshape = np.array(patchshape)
     rad = np.array([p // 2 for p in patchshape])
     ret_inter = kwargs.get('return_intermediates', False)

@@ -150,20 +150,24 @@ def test_edge_even_patchshape_rejected():
 def full():
     import torch
     import bench
+    from patchperpix_b200 import synth
     from patchperpix_b200.assembly import BlockAssembler
     dev = torch.device('cuda', 0)
-    ps = np.array(bench.WORKLOAD['patchshape'])
-    pred, numinst, _ = bench.make_inputs(dev, bench.WORKLOAD['seed'])
+    # BASELINE configs[1] at its full size: 2-D worms 696x520, patchshape 1x41x41
+    ps = np.array([1, 41, 41])
+    labels, numinst = synth.worms_2d((520, 696), n_worms=40, seed=2)
+    pred = synth.patches_from_labels(labels, ps, seed=2, device=dev)
     P = int(np.prod(ps))
     fg = (pred[P // 2] > 0.5).to(torch.uint8)
     overlap = torch.from_numpy((numinst > 1).astype(np.uint8)).to(dev)
     mask = fg.clone()
     mask[overlap > 0] = 0
-    asm = BlockAssembler(pred, fg, overlap, ps, **bench.KW)
+    kw = dict(bench.KW, blockwise=False)
+    asm = BlockAssembler(pred, fg, overlap, ps, **kw)
     asm.prepare()
     asm.consensus(want_cnt=True)
     asm.rank()
-    return dict(pred=pred, fg=fg, overlap=overlap, mask=mask, asm=asm, ps=ps, kw=bench.KW)
+    return dict(pred=pred, fg=fg, overlap=overlap, mask=mask, asm=asm, ps=ps, kw=kw)
 
 
 def _shift(t, dy, dx):

@@ -203,6 +203,109 @@ class Recorder:
             self.d['pairs'] = np.array(arrs[3])
 
 
+# BASELINE-size cases (parity was pinned at toy sizes only).  Too big for
+# the dense snapshots of run_case: the recorder keeps a row sample + whole-array sums.
+BIG_CASES = {
+    # configs[1] at its full size: the 2-D worms image, 1x41x41 patches
+    'worms2d_c2_full': (dict(kind='worms', seed=2, shape=(520, 696), n_worms=40),
+                        (1, 41, 41), {}, 48),
+    # configs[2]-shaped block: nuclei-like blobs, 5x21x21 patches, 16x128x128
+    'blobs3d_c3_block': (dict(kind='blobs', seed=3, shape=(16, 128, 128), n=20,
+                              rad_xy=(6, 14), rad_z=(2, 4)),
+                         (5, 21, 21), {}, 32),
+}
+
+
+class BigRecorder:
+    """like Recorder, but keeps only `rows` of the compact consensus arrays and
+    double-precision sums (the dense arrays are tens of GB)."""
+
+    def __init__(self, gate, ps, rows):
+        self.gate, self.ps, self.rows = gate, ps, rows
+        self.d = {}
+
+    def _keep(self, key, arr):
+        self.d[key + '_sum'] = np.float64(np.asarray(arr).astype(np.float64).sum())
+        full = layout.dense_to_compact(np.asarray(arr), self.gate, self.ps)
+        assert np.isclose(full.astype(np.float64).sum(), self.d[key + '_sum'],
+                          rtol=1e-9, atol=1e-6), key
+        self.d[key] = full[self.rows].copy()
+
+    def __call__(self, kind, options, args):
+        arrs = [a for a in args]
+        if kind == 'K_FILL':
+            if '-DOUTPUT_CNT' in options:
+                self._keep('cnt', arrs[-1])
+            else:
+                self._keep('cons_raw', arrs[-1])
+        elif kind == 'K_NORM':
+            self._keep('cons_norm', arrs[1])
+        elif kind == 'K_RANK':
+            self.d['score'] = np.array(arrs[-1])
+        elif kind == 'K_GRAPH':
+            self.d['aff'] = np.asarray(arrs[2])
+            self.d['pairs'] = np.array(arrs[3])
+
+
+def run_big(name):
+    import hashlib
+    skw, ps, over, max_rows = BIG_CASES[name]
+    ps = np.array(ps)
+    pred, numinst, labels = synth.make_case(patchshape=ps, **skw)
+    mid = int(np.prod(ps)) // 2
+    gate0 = (pred[mid] > 0.5) & ~(numinst > 1)
+    rows = np.sort(np.random.default_rng(0).choice(int(gate0.sum()), max_rows, replace=False))
+    rec = BigRecorder(gate0, ps, rows)
+    S = ref_runner.RefSession(recorder=rec)
+    kw = S.default_kwargs(**over)
+    fg = pred[mid] > kw['patch_threshold']
+    stages = {}
+    vi = S.vi
+    orig_cover = S.mods['foreground_cover'].computeForegroundCover
+    orig_thin = S.mods['foreground_cover'].thinOutForegroundCover
+    orig_rank = S.mods['ranked_patches'].rank_patches_by_score
+
+    def cover(*a, **k):
+        res = orig_cover(*a, **k)
+        stages['cover'] = np.array([p[0] for p in res[0]], np.int32).reshape(-1, 3)
+        return res
+
+    def thin(*a, **k):
+        res = orig_thin(*a, **k)
+        stages['thin'] = np.array([p[0] for p in res[0]], np.int32).reshape(-1, 3)
+        return res
+
+    def rank(*a, **k):
+        res = orig_rank(*a, **k)
+        stages['ranked'] = np.array([p[0] for p in res], np.int32).reshape(-1, 3)
+        return res
+    vi.computeForegroundCover = cover
+    vi.thinOutForegroundCover = thin
+    S.mods['ranked_patches'].rank_patches_by_score = rank
+    t0 = time.time()
+    inst, fgo = vi.to_instance_seg(pred, fg.copy(), fg.copy(), numinst.copy(), ps.copy(), **kw)
+    dt = time.time() - t0
+    sn = rec.d
+    out = dict(
+        pred_sha1=hashlib.sha1(pred.astype(np.float16).tobytes()).hexdigest(), numinst=numinst,
+        patchshape=ps.astype(np.int32),
+        kwargs=json.dumps({k: v for k, v in kw.items()
+                           if isinstance(v, (bool, int, float, str))}),
+        synth=json.dumps({k: (list(v) if isinstance(v, tuple) else v) for k, v in skw.items()}),
+        instances=inst, gate=gate0, rows=rows.astype(np.int32),
+        cons_raw=sn['cons_raw'], cons_raw_sum=sn['cons_raw_sum'],
+        cnt=sn['cnt'].astype(np.uint16), cnt_sum=sn['cnt_sum'],
+        cons_norm=sn['cons_norm'], cons_norm_sum=sn['cons_norm_sum'],
+        score=sn['score'], pairs=sn['pairs'], aff=np.array(sn['aff']),
+        ranked_sha1=hashlib.sha1(stages['ranked'].tobytes()).hexdigest(),
+        ranked_head=stages['ranked'][:4096], cover=stages['cover'], thin=stages['thin'])
+    fn = os.path.join(GOLD, name + '.npz')
+    np.savez_compressed(fn, **out)
+    print('%-24s %6.1fs  fg=%d rows=%d pairs=%d inst=%d  %.2f MB' % (
+        name, dt, int(fg.sum()), len(rows), len(sn['pairs']), len(np.unique(inst)) - 1,
+        os.path.getsize(fn) / 1e6), flush=True)
+
+
 def run_blockwise(S, mws=False):
     """the reference's blockwise driver (stitch_patch_graph.main) on an
     in-memory zarr stand-in (oracle/ref_runner.FakeGroup).  mws: only return
@@ -251,6 +354,51 @@ def run_blockwise(S, mws=False):
     print('%-24s %6.1fs  blocks+faces=%d inst=%d  %.2f MB' % (
         'blockwise3d_ps5', dt, len(blk.d) // 2, len(np.unique(res['instances'])) - 1,
         os.path.getsize(fn) / 1e6))
+
+
+def run_blockwise_big(S):
+    """the reference's blockwise driver on a 3x3x3 block grid with the mutex-watershed
+    partition (the flylight default): labels only."""
+    import hashlib
+    import shutil
+    sp = ref_runner.load_stitch_module(S)
+    ps = np.array([5, 5, 5])
+    skw = dict(kind='neurites', seed=23, shape=(36, 66, 66), n=14, radius=(1.5, 2.5),
+               seg_len=9.0, n_seg=10)
+    pred, numinst, labels = synth.make_case(patchshape=ps, **skw)
+    root = '/tmp/ppp_gold_blk3'
+    shutil.rmtree(root, ignore_errors=True)
+    pred_path = os.path.join(root, 'sample.zarr')
+    store = ref_runner.FakeGroup.open(pred_path, 'w')
+    store['volumes/pred_affs'] = pred.astype(np.float16)
+    prob = np.stack([(numinst == 0), (numinst == 1), (numinst > 1)]).astype(np.float32)
+    store['volumes/pred_numinst'] = prob
+    res = {}
+    for mws in (True, False):
+        kw = S.default_kwargs(
+            blockwise=True, chunksize=[12, 22, 22], patchshape=[5, 5, 5],
+            aff_key='volumes/pred_affs', numinst_key='volumes/pred_numinst', fg_key=None,
+            numinst_threshs=[0.9, 0.1], only_bb=False, output_format='hdf',
+            num_parallel_blocks=1, ignore_small_comps=0, skeletonize_foreground=False,
+            remove_small_comps=0, res_key='vote_instances', mws=mws)
+        del kw['result_folder']
+        out_dir = os.path.join(root, 'out_mws' if mws else 'out_cc')
+        t0 = time.time()
+        sp.main(pred_path, result_folder=out_dir, **kw)
+        dt = time.time() - t0
+        out = ref_runner.FakeGroup.open(os.path.join(out_dir, 'sample.hdf'))
+        res['instances_mws' if mws else 'instances_cc'] = np.asarray(out['vote_instances'])
+        print('blockwise 3x3x3 mws=%s %.1fs inst=%d' % (
+            mws, dt, len(np.unique(np.asarray(out['vote_instances']))) - 1), flush=True)
+    res.update(
+        pred_sha1=hashlib.sha1(pred.astype(np.float16).tobytes()).hexdigest(),
+        numinst=numinst, patchshape=ps.astype(np.int32),
+        kwargs=json.dumps({k: v for k, v in kw.items()
+                           if isinstance(v, (bool, int, float, str, list)) or v is None}),
+        synth=json.dumps({k: (list(v) if isinstance(v, tuple) else v) for k, v in skw.items()}))
+    fn = os.path.join(GOLD, 'blockwise3d_3x3x3_mws.npz')
+    np.savez_compressed(fn, **res)
+    print('blockwise3d_3x3x3_mws %.2f MB' % (os.path.getsize(fn) / 1e6))
 
 
 def run_mws(S):
@@ -365,9 +513,16 @@ def main():
     if sys.argv[1:] == ['mws']:
         run_mws(ref_runner.RefSession())
         return 0
+    if sys.argv[1:] == ['blockwise3']:
+        run_blockwise_big(ref_runner.RefSession())
+        return 0
     if sys.argv[1:] == ['blockwise']:
         S = ref_runner.RefSession()
         run_blockwise(S)
+        return 0
+    if sys.argv[1:] and all(n in BIG_CASES for n in sys.argv[1:]):
+        for n in sys.argv[1:]:
+            run_big(n)
         return 0
     names = sys.argv[1:] or list(CASES)
     rec = Recorder()
