@@ -258,6 +258,18 @@ def _face_job(shard, candidates, pa, ps, kwargs, block_fn=None):
     return overlapping.astype(np.uint32), np.asarray(aff, np.float32)
 
 
+def _box_dilate(vol, size):
+    """dilation of a [1,1,Z,Y,X] indicator by a box of odd `size`, one axis at a time"""
+    import torch
+    for ax in range(3):
+        k = [1, 1, 1]
+        k[ax] = size[ax]
+        if size[ax] > 1:
+            vol = torch.nn.functional.max_pool3d(vol, kernel_size=tuple(k), stride=1,
+                                                 padding=tuple(v // 2 for v in k))
+    return vol
+
+
 def _face_batch(shard, faces, ps, kwargs):
     """the face jobs `faces` = [(job, (candidates, pair index array))] as ONE pass over
     the bounding box of their regions.  Returns {job: (pairs u32 [n,6] volume coordinates,
@@ -295,13 +307,11 @@ def _face_batch(shard, faces, ps, kwargs):
     cen = torch.from_numpy(cen[ok]).to(dev)
     seed = torch.zeros((1, 1) + bshape, dtype=torch.float32, device=dev)
     seed[0, 0, cen[:, 0], cen[:, 1], cen[:, 2]] = 1.0
-    win = torch.nn.functional.max_pool3d(seed, kernel_size=tuple(int(p) for p in ps), stride=1,
-                                         padding=tuple(int(r) for r in margin))
+    win = _box_dilate(seed, [int(p) for p in ps])
     rv_l = asm.rowvox.long()
     need = win.reshape(-1)[rv_l].to(torch.uint8).contiguous()
     # their partners (anything within 2*ps-1) must have tables too
-    win2 = torch.nn.functional.max_pool3d(win, kernel_size=tuple(int(2 * p - 1) for p in ps),
-                                          stride=1, padding=tuple(int(p - 1) for p in ps))
+    win2 = _box_dilate(win, [int(2 * p - 1) for p in ps])
     asm.received(win2.reshape(-1)[rv_l].to(torch.uint8).contiguous())
     asm.consensus(need=need)
     aff_all = np.zeros(0, np.float32)

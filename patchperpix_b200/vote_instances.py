@@ -160,9 +160,12 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
             sc = sc[ok]
             seed = torch.zeros((1, 1) + shape, dtype=torch.float32, device=asm.dev)
             seed[0, 0, sc[:, 0], sc[:, 1], sc[:, 2]] = 1.0
-            win = torch.nn.functional.max_pool3d(
-                seed, kernel_size=tuple(int(p) for p in patchshape), stride=1,
-                padding=tuple(int(r) for r in rad))
+            win = seed
+            for ax in range(3):                      # box dilation, one axis at a time
+                k = [1, 1, 1]
+                k[ax] = int(patchshape[ax])
+                win = torch.nn.functional.max_pool3d(win, kernel_size=tuple(k), stride=1,
+                                                     padding=tuple(v // 2 for v in k))
             need = win.reshape(-1)[asm.rowvox.long()].to(torch.uint8).contiguous()
         asm.consensus(need=need)
     if kwargs.get('save_consensus', False):

@@ -281,6 +281,12 @@ def test_single_block_entry_point_with_flylight_toml(tmp_path):
     kw = flylight_kwargs(blockwise=False)
     kw.update(blockwise=False, return_intermediates=False, affinities=path,
               result_folder=str(tmp_path / 'out1'), check_required=False)
+    # DOCUMENTED DEVIATION: outside the blockwise driver the reference thins the mask to
+    # cover to its 3-D skeleton (vote_instances.py:220-224, skimage); that key is refused
+    # by name here, the blockwise driver (the flylight default) never reads it
+    with pytest.raises(NotImplementedError, match='skeletonize_foreground'):
+        vi.main(**kw)
+    kw['skeletonize_foreground'] = False
     vi.main(**kw)
     res = np.load(os.path.join(kw['result_folder'], 'sample.npz'))
     p16 = pred.astype(np.float16).astype(np.float32)

@@ -32,6 +32,19 @@ def _load():
     return g, kw, pred, numinst
 
 
+def _load3():
+    """3x3x3 blocks, reference run with the mutex watershed and with thresholded CC"""
+    g = dict(np.load(os.path.join(gu.GOLD, 'blockwise3d_3x3x3_mws.npz')))
+    kw = json.loads(str(g['kwargs']))
+    skw = json.loads(str(g['synth']))
+    for k in gu._TUPLES:
+        if k in skw:
+            skw[k] = tuple(skw[k])
+    pred, numinst, _ = synth.make_case(patchshape=g['patchshape'], **skw)
+    assert hashlib.sha1(pred.astype(np.float16).tobytes()).hexdigest() == str(g['pred_sha1'])
+    return g, kw, pred, numinst
+
+
 def rows_of(pred, numinst, th, axis, lo, hi):
     """compact rows of the slab [lo, hi) of a dense prediction: the voxels whose
     centre channel passes the threshold (what a ppp+dec run would have decoded)."""
@@ -148,9 +161,32 @@ def test_sharded_gloo(world):
     assert sum(r[3] for r in res) > 0, "no halo rows were exchanged"
 
 
+def test_sharded_3x3x3_blocks_cc_oracle_engine():
+    g, kw, pred, numinst = _load3()
+    inst, info, _, _ = _run_rank(pred, numinst, dict(kw, mws=False), 0, 1)
+    assert info['n_blocks'] == 27
+    assert np.array_equal(inst.numpy().astype(np.uint16), g['instances_cc'])
+
+
 # ---------------------------------------------------------------------------
 # GPU
 # ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize('mws', [True, False])
+def test_3x3x3_blocks_cuda_matches_reference_run(mws):
+    """27 blocks, 54 faces: the sharded rows driver and the dense driver both reproduce
+    the labels of the reference's own blockwise run."""
+    g, kw, pred, numinst = _load3()
+    want = g['instances_mws' if mws else 'instances_cc']
+    inst, info, _, _ = _run_rank(pred, numinst, dict(kw, mws=mws), 0, 1, hooks=False,
+                                 device='cuda', workers=4)
+    assert info['n_blocks'] == 27
+    assert np.array_equal(inst.cpu().numpy().astype(np.uint16), want)
+    prob = np.stack([(numinst == 0), (numinst == 1), (numinst > 1)]).astype(np.float32)
+    dense, _, _ = spg.stitch_arrays(spg.VolumeInputs(pred.astype(np.float16), numinst_prob=prob),
+                                    **dict(kw, mws=mws))
+    assert np.array_equal(dense.astype(np.uint16), want)
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('mws', [False, True])
 def test_sharded_cuda_matches_reference_golden(mws):
