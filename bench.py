@@ -239,6 +239,136 @@ def run_reference_arm(args):
     return 0
 
 
+def run_refgpu_arm(args):
+    """--impl refgpu: the UNMODIFIED reference kernels compiled for sm_100a
+    (oracle/_ref/refk_cuda_*.so), launched with the reference's geometry -- (8,8,8)
+    blocks, one thread per voxel, 512 patch pairs per launch with a sync in between
+    (utilVoteInstances.py:452-462, aff_patch_graph.py:137-159) -- on the sample region
+    of the bench volume, next to this build's kernels on the same region.  The host
+    steps between the kernels (cover, thinning, pairs, labels) are the oracle's, as in
+    the CPU arm; kernel times are reported separately."""
+    import torch
+    from oracle import ref_runner, host_logic
+    from patchperpix_b200 import cuda_code as cc, vote_instances as vi
+    from patchperpix_b200.assembly import RowSource
+    if int(os.environ.get('RANK', '0')) != 0:
+        return 0
+    w = workload_from_args(args)
+    ps = tuple(int(p) for p in w['patchshape'])
+    pred_np, ni_np, start = sample_region(w)
+    dims = pred_np.shape[1:]
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(0)
+    base = ['-DUSE_LESS_THAN_TH', '-DOVERLAP']
+    th = KW['patch_threshold']
+    ks = {}
+    for kind, flags in (('fill', base + ['-DNORM_PROB_PRODUCT']),
+                        ('cnt', base + ['-DNORM_PROB_PRODUCT', '-DOUTPUT_CNT']),
+                        ('norm', []), ('rank', base + ['-DNORM_PATCH_RANK']),
+                        ('graph', ['-DNORM_PATCH_AFFINITY'])):
+        so = ref_runner.build_ref_kernel_cuda('fill' if kind == 'cnt' else kind, dims, ps, th,
+                                              flags)
+        ks[kind] = ref_runner.load_ref_kernel_cuda(so)
+    ns = [2 * p for p in ps]
+    Z, Y, X = dims
+    grid = ((X + 7) // 8, (Y + 7) // 8, (Z + 7) // 8)
+    blk = (8, 8, 8)
+    P = int(np.prod(ps))
+    fg = pred_np[P // 2] > np.float32(th)
+    overlap_np = np.ascontiguousarray(ni_np > 1)
+    pred = torch.from_numpy(pred_np).to(dev)
+    overlap = torch.from_numpy(overlap_np).to(dev)
+    rad = np.array(ps) // 2
+    times = []
+    kms = {}
+    inst = None
+    for it in range(args.warmup + args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        km = {}
+
+        def timed(name, fn, *a, **k):
+            t = time.perf_counter()
+            fn(*a, **k)
+            km[name] = km.get(name, 0.0) + (time.perf_counter() - t) * 1e3
+        cons = torch.zeros(tuple(ns) + dims, dtype=torch.float32, device=dev)
+        cnt = torch.zeros(tuple(ns) + dims, dtype=torch.float32, device=dev)
+        timed('fill', ks['fill'], pred.data_ptr(), overlap.data_ptr(), cons.data_ptr(),
+              block=blk, grid=grid)
+        timed('fill_cnt', ks['cnt'], pred.data_ptr(), overlap.data_ptr(), cnt.data_ptr(),
+              block=blk, grid=grid)
+        timed('norm', ks['norm'], pred.data_ptr(), cons.data_ptr(), cnt.data_ptr(),
+              block=blk, grid=grid)
+        del cnt
+        score = torch.zeros(dims, dtype=torch.float32, device=dev)
+        timed('rank', ks['rank'], pred.data_ptr(), cons.data_ptr(), overlap.data_ptr(),
+              score.data_ptr(), block=blk, grid=grid)
+        score_np = score.cpu().numpy()
+        allp = host_logic.interior_patches(fg, rad)
+        ranked = host_logic.rank_by_score(allp, score_np)
+        mask = fg.copy()
+        mask[overlap_np] = 0
+        fc = np.float32(KW['fc_threshold'])
+        sel = host_logic.foreground_cover(1 * overlap_np, mask, np.array(ps), ranked, rad,
+                                          pred_np, fc)
+        sel = host_logic.thin_cover(mask, sel, np.array(ps), rad, pred_np, fc)
+        pairs = host_logic.patch_pairs(sel, np.array(ps), True, 2)
+        inst = np.zeros(dims, np.uint16)
+        if pairs is not None:
+            n = len(pairs)
+            pd = torch.from_numpy(np.ascontiguousarray(pairs).view(np.int32)).to(dev)
+            aff = torch.zeros(n, dtype=torch.float32, device=dev)
+            for i in range(0, n, 512):
+                nb = min(512, n - i)
+                timed('graph', ks['graph'], pred.data_ptr(), cons.data_ptr(), aff.data_ptr(),
+                      pd.data_ptr(), np.uint64(nb), np.int32(i),
+                      block=(min(512, n), 1, 1), grid=((nb + min(512, n) - 1) // min(512, n), 1, 1))
+            inst, _ = host_logic.label_instances(pairs, aff.cpu().numpy(), pred_np, np.array(ps),
+                                                 rad, dims, np.float32(th))
+        del cons
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            for k, v in km.items():
+                kms[k] = kms.get(k, 0.0) + v / args.steps
+    nfg = int(fg.sum())
+    # this build's kernels on the same region (events around every C-ABI call)
+    c = np.argwhere(fg)
+    v2r = torch.full(fg.shape, -1, dtype=torch.int32)
+    v2r[c[:, 0], c[:, 1], c[:, 2]] = torch.arange(len(c), dtype=torch.int32)
+    rows = torch.from_numpy(np.ascontiguousarray(
+        pred_np[:, c[:, 0], c[:, 1], c[:, 2]].T.astype(np.float16)))
+    src = RowSource(rows.to(dev), v2r.to(dev))
+    fg_t = torch.from_numpy(fg.astype(np.uint8)).to(dev)
+    ni_t = torch.from_numpy(ni_np).to(dev)
+    kw1 = dict(KW, blockwise=False, ppp_latency_stream=False)
+    for _ in range(2):
+        inst_gpu, _ = vi.to_instance_seg(src, fg_t, fg_t.clone(), ni_t, np.array(ps), **kw1)
+    with CallTimer(cc, torch) as ct:
+        inst_gpu, _ = vi.to_instance_seg(src, fg_t, fg_t.clone(), ni_t, np.array(ps), **kw1)
+    ours = {k: round(v['ms'], 4) for k, v in ct.calls.items()}
+    ours_kernels = sum(v for k, v in ours.items())
+    ref_kernels = sum(kms.values())
+    ms = 1e3 * float(np.mean(times))
+    sample = 'region %s at %s of the volume (%d fg voxels), single block' % (
+        'x'.join(str(s) for s in dims), tuple(int(v) for v in start), nfg)
+    line = dict(metric='consensus+assembly fg Mvoxels/s', value=nfg / (ms * 1e-3) / 1e6,
+                unit='Mvoxels/s', n_gpus=1, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling='strong', vs_baseline=None,
+                dtype='f32', data='synthetic', impl='refgpu',
+                config=dict(workload=workload_name(w), sample=sample,
+                            note='unmodified reference .cu kernels, nvcc sm_100a, reference launch '
+                                 'geometry; host steps = oracle python (cover / thinning dominate '
+                                 'ms_per_step)'),
+                reference_kernel_ms={k: round(v, 4) for k, v in kms.items()},
+                reference_kernels_total_ms=ref_kernels,
+                ours_call_ms=ours, ours_total_ms=ours_kernels,
+                kernel_time_ratio=ref_kernels / ours_kernels if ours_kernels else None,
+                labels_identical=bool(np.array_equal(inst, inst_gpu)))
+    print(json.dumps(line))
+    return 0
+
+
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
@@ -294,7 +424,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'refgpu'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--shape', default=None, help='z,y,x (default: the FlyLight-sized volume)')
     ap.add_argument('--chunk', default=None, help='z,y,x chunksize')
@@ -303,6 +433,8 @@ def main():
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
+    if args.impl == 'refgpu':
+        return run_refgpu_arm(args)
 
     import torch
     import torch.distributed as dist

@@ -19,11 +19,17 @@ for dims, ps in (((1, 160, 160), (1, 41, 41)), ((1, 256, 256), (1, 41, 41)), ((2
         ]
 
 
+# the same kernels for sm_100a (bench.py --impl refgpu), on the sample both arms share
+CUDA_CONFIGS = [c[:5] for c in CONFIGS if c[1] == (72, 72, 72) and not c[5]]
+
+
 def build_all():
     if not ref_runner.reference_available():
         print('reference sources absent: keeping prebuilt oracle/_ref')
         return []
-    return [ref_runner.build_ref_kernel(*c) for c in CONFIGS]
+    out = [ref_runner.build_ref_kernel(*c) for c in CONFIGS]
+    out += [ref_runner.build_ref_kernel_cuda(*c) for c in CUDA_CONFIGS]
+    return out
 
 
 if __name__ == '__main__':

@@ -132,6 +132,69 @@ def build_ref_kernel(kind, dims, patchshape, th, flags=(), omp=False):
     return so
 
 
+def build_ref_kernel_cuda(kind, dims, patchshape, th, flags=()):
+    """the same reference .cu file compiled by nvcc for sm_100a (unmodified, read in
+    place) with a launcher that uses the reference's launch geometry: the "existing GPU
+    implementation" timed beside ours (bench.py --impl refgpu).  Returns the path of
+    oracle/_ref/refk_cuda_*.so (prebuilt here, travels to the GPU box)."""
+    fn = {'fill': 'fillConsensusArray.cu', 'norm': 'normConsensusArray.cu',
+          'rank': 'rankPatches.cu', 'graph': 'computePatchGraph.cu'}[kind]
+    ps = [int(p) for p in patchshape]
+    ns = [2 * p if (ps[0] > 1 or i > 0) else p for i, p in enumerate(ps)]
+    thi = th if th < 0.5 else 1.0 - th
+    tag = '%s_%dx%dx%d_%dx%dx%d_%s_%s' % (
+        kind, dims[0], dims[1], dims[2], ps[0], ps[1], ps[2], repr(th),
+        '-'.join(sorted(f.replace('-D', '') for f in flags)) or 'none')
+    so = os.path.join(REF_OUT, 'refk_cuda_' + tag + '.so')
+    if os.path.exists(so):
+        return so
+    if not reference_available():
+        raise FileNotFoundError('%s not prebuilt and %s is absent' % (so, REF_ROOT))
+    defs = ['-DDATAZSIZE=%d' % dims[0], '-DDATAYSIZE=%d' % dims[1],
+            '-DDATAXSIZE=%d' % dims[2],
+            '-DPSZ=%d' % ps[0], '-DPSY=%d' % ps[1], '-DPSX=%d' % ps[2],
+            '-DNSZ=%d' % ns[0], '-DNSY=%d' % ns[1], '-DNSX=%d' % ns[2],
+            '-DTH=%s' % repr(th), '-DTHI=%s' % repr(thi),
+            '-DL_Z=%d' % dims[0], '-DL_Y=%d' % dims[1], '-DL_X=%d' % dims[2],
+            '-DL_NSY=%d' % ns[1], '-DL_NSX=%d' % ns[2],
+            '-D' + {'fill': 'K_FILL', 'norm': 'K_NORM', 'rank': 'K_RANK',
+                    'graph': 'K_GRAPH'}[kind]] + list(flags)
+    os.makedirs(REF_OUT, exist_ok=True)
+    src = so[:-3] + '.cu'
+    with open(src, 'w') as f:
+        f.write('#include <cstdint>\n#include "%s"\n#include "launchers_cuda.inc"\n' %
+                os.path.join(REF_VI, 'cuda', fn))
+    cmd = ['/usr/local/cuda/bin/nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3',
+           '-shared', '-Xcompiler', '-fPIC', '-w', '-I', SHIM] + defs + [src, '-o', so]
+    subprocess.run(cmd, check=True)
+    os.remove(src)
+    return so
+
+
+def load_ref_kernel_cuda(so_path):
+    """callable(*device pointers / numpy scalars, block=, grid=) -> cudaError_t"""
+    lib = ctypes.CDLL(so_path)
+    fn = lib.ppp_ref_launch
+    fn.restype = ctypes.c_int
+
+    def launch(*args, block=None, grid=None):
+        keep = []
+        ptrs = (ctypes.c_void_p * len(args))()
+        for i, a in enumerate(args):
+            if isinstance(a, int):
+                ptrs[i] = a
+            else:
+                arr = np.array([a])
+                keep.append(arr)
+                ptrs[i] = arr.ctypes.data
+        grid = tuple(int(g) for g in grid) + (1,) * (3 - len(grid))
+        block = tuple(int(b) for b in block) + (1,) * (3 - len(block))
+        rc = fn(ptrs, *[ctypes.c_uint(v) for v in grid + block])
+        if rc != 0:
+            raise RuntimeError('reference kernel failed: cudaError %d' % rc)
+    return launch
+
+
 def load_ref_kernel(so_path):
     return _Kernel(so_path)
 

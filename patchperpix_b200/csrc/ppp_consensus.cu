@@ -386,11 +386,14 @@ consensus_small_kernel(const float* __restrict__ rv, const uint16_t* __restrict_
             if (!m || cfg.prod_mode == 0) continue;
             const float* __restrict__ r1 = s_rv + w1 * g.psx;
             const float* __restrict__ r2 = rvp + w2 * g.psx - ox;
-            while (m) {
-                const int tb = __ffs((int)m) - 1;
-                m &= m - 1;
-                sum = fmaf(r1[tb], __ldg(r2 + tb), sum);
-            }
+            // all partner values of the line first (independent, predicated loads in
+            // flight together), then the multiply-adds in centre order
+            float p2v[8];
+#pragma unroll
+            for (int tb = 0; tb < 8; tb++) p2v[tb] = ((m >> tb) & 1u) ? __ldg(r2 + tb) : 0.0f;
+#pragma unroll
+            for (int tb = 0; tb < 8; tb++)
+                if ((m >> tb) & 1u) sum = fmaf(r1[tb], p2v[tb], sum);
         }
         cons[row * g.K + k] = consensus_epilogue(cfg, sum, pos, neg);
         cnt[row * g.K + k] = ((uint32_t)neg << 16) | (uint32_t)pos;

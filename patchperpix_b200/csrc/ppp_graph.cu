@@ -275,7 +275,10 @@ patch_graph_ref_kernel(Src pred, const uint8_t* __restrict__ flags,
                           (uint32_t)(y2c - oy_) * (uint32_t)(x1c - ox_) * (uint32_t)(x2c - ox_);
     // patches further apart than 2*ps on an axis share no slot: every term is skipped
     // by the offset test (:98-101), sum and count stay 0
-    if (abs(z2c - z1c) > 2 * g.psz || abs(y2c - y1c) > 2 * g.psy || abs(x2c - x1c) > 2 * g.psx) {
+    // (two window pixels are at least |delta| - 2*(ps//2) apart; beyond ps - 1 the slot index
+    // falls outside the cube and the term is zero, :98-101, so the sum is exactly 0)
+    if (abs(z2c - z1c) > 2 * (g.psz - 1) || abs(y2c - y1c) > 2 * (g.psy - 1) ||
+        abs(x2c - x1c) > 2 * (g.psx - 1)) {
         if (tid == 0) aff[id] = 0.0f;
         return;
     }

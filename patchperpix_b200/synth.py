@@ -318,6 +318,20 @@ def patches_from_labels(labels, patchshape, seed=0, noise=0.04, hard_frac=0.0,
     return pred
 
 
+def crop_case(labels, patchshape=(7, 7, 7), seed=31, hard_frac=0.1):
+    """predictions around a given label volume (BASELINE configs[0]: the ground truth of
+    the bundled flylight crop), nothing within patchshape//2 of the border."""
+    ps = np.array(patchshape)
+    pred = patches_from_labels(np.asarray(labels).astype(np.int32), ps, seed=seed,
+                               hard_frac=hard_frac)
+    r = ps // 2
+    inner = np.zeros(labels.shape, bool)
+    inner[r[0]:labels.shape[0] - r[0], r[1]:labels.shape[1] - r[1],
+          r[2]:labels.shape[2] - r[2]] = True
+    pred[:, ~inner] = 0
+    return pred
+
+
 def make_case(kind, patchshape, seed=0, hard_frac=0.0, noise=0.04, shape=None,
               device=None, **kw):
     """(pred f32 [P,Z,Y,X], numinst u8 [Z,Y,X], labels i32 [Z,Y,X])."""

@@ -12,7 +12,8 @@ from patchperpix_b200 import synth
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 # BASELINE-size cases (tools/gen_golden.py BIG_CASES): row samples + checksums, compared on
 # the GPU only (tests/test_gpu_big_golden.py) -- the CPU oracle would need minutes on them
-BIG = ('worms2d_c2_full', 'blobs3d_c3_block', 'blockwise3d_3x3x3_mws')
+BIG = ('worms2d_c2_full', 'blobs3d_c3_block', 'blockwise3d_3x3x3_mws', 'c1_cpu_consensus',
+       'flylight_default_kwargs')
 NAMES = sorted(os.path.basename(f)[:-4]
                for f in glob.glob(os.path.join(GOLD, '*.npz'))
                if not os.path.basename(f).startswith(('blockwise', 'mws_', 'chan_'))

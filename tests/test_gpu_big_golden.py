@@ -65,3 +65,37 @@ def test_every_stage_against_the_reference_run(name):
     # and the whole path through the entry point, own scores and affinities
     inst, _ = vi.to_instance_seg(pred, fg, fg.copy(), g['numinst'], ps, **kw)
     assert np.array_equal(inst, g['instances'])
+
+
+def test_c1_counters_equal_the_reference_cpu_path():
+    """BASELINE configs[0] / SURVEY.md A.8: the reference's PYTHON CPU path
+    (fillLookup -> computeFGBGsets -> create_consensus_array, run unmodified by
+    tools/gen_c1_cpu.py on the bundled flylight crop) accumulates +1 / -1 votes in int16;
+    with plain vote counting, the inverse-threshold background band and no overlap
+    handling the CUDA path's counters must give exactly pos - neg."""
+    import hashlib
+    import torch
+    from patchperpix_b200 import synth
+    from patchperpix_b200.assembly import BlockAssembler
+    from patchperpix_b200.consensus_array import ConsensusArray
+    g = np.load(os.path.join(gu.GOLD, 'c1_cpu_consensus.npz'))
+    ps = np.array([7, 7, 7])
+    pred = synth.crop_case(g['labels'], ps, seed=int(g['seed']))
+    assert hashlib.sha1(pred.astype(np.float16).tobytes()).hexdigest() == str(g['pred_sha1'])
+    th = float(g['th'])
+    kw = dict(patch_threshold=th, fc_threshold=0.5, vi_bg_use_inv_th=True,
+              consensus_norm_prob_product=False, consensus_prob_product=False,
+              consensus_norm_aff=False, consensus_interleaved_cnt=False, overlapping_inst=False)
+    predt = torch.from_numpy(pred).cuda()
+    fg = (predt[171] > th).to(torch.uint8)
+    for impl in (0, 2):                                  # received tables, bit-guided gather
+        asm = BlockAssembler(predt, fg, torch.zeros_like(fg), ps, **kw)
+        asm.prepare(want_rbits=True)
+        asm.consensus(want_cnt=True, impl=impl)
+        ca = ConsensusArray(asm)
+        votes = ca.compact('pos').astype(np.int64) - ca.compact('neg').astype(np.int64)
+        assert np.array_equal(votes[g['rows']], g['cons'].astype(np.int64)), impl
+        assert int(votes.sum()) == int(g['cons_sum'])
+        assert int(np.abs(votes).sum()) == int(g['cons_abs_sum'])
+        # counter mode: the consensus array itself is that difference
+        assert np.array_equal(ca.compact('cons')[g['rows']], g['cons'].astype(np.float32))

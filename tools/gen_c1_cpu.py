@@ -32,15 +32,7 @@ SEED = 31
 
 def c1_inputs(labels):
     """predictions of the C1 case from its label volume (also used by the test)."""
-    ps = np.array([7, 7, 7])
-    pred = synth.patches_from_labels(labels.astype(np.int32), ps, seed=SEED, hard_frac=0.1)
-    # nothing within patchshape//2 of the border: the reference's lookup table is only
-    # filled for interior foreground voxels (utilVoteInstances.py:49-54)
-    r = 3
-    inner = np.zeros(labels.shape, bool)
-    inner[r:-r, r:-r, r:-r] = True
-    pred[:, ~inner] = 0
-    return pred
+    return synth.crop_case(labels, (7, 7, 7), seed=SEED, hard_frac=0.1)
 
 
 def main():
