@@ -114,28 +114,48 @@ def synth_kw(w):
 # ---------------------------------------------------------------------------
 # the bounded sample both arms can afford: a region of the same volume
 # ---------------------------------------------------------------------------
-def sample_region(w):
-    """a CPU_SAMPLE-sized box of the volume around a neurite (deterministic)."""
+CPU_REGIONS = 12                # regions the CPU arm assembles per step (about 10 s of host work)
+
+
+def sample_regions(w, n=CPU_REGIONS):
+    """n CPU_SAMPLE-sized boxes of the volume, each around the start of a neurite
+    (deterministic): [(pred f32 [P,z,y,x], numinst u8 [z,y,x], start)]."""
     from patchperpix_b200 import synth
     shape = np.asarray(w['shape'])
     size = np.minimum(np.asarray(CPU_SAMPLE), shape)
-    # first polyline point of the generator's random sequence that lies inside
-    rng = np.random.default_rng(w['seed'])
-    p = np.array([rng.uniform(0, shape[0]), rng.uniform(0, shape[1]), rng.uniform(0, shape[2])])
-    start = np.clip(p.astype(int) - size // 2, 0, shape - size)
-    # labels of a slab window around it, dense patches of the region
     ps = w['patchshape']
-    lo, hi = int(start[0]), int(start[0] + size[0])
-    coords, patches, numinst = synth.neurite_rows(w['shape'], ps, axis=0, lo=lo, hi=hi,
-                                                  device='cpu', box=(start, start + size),
-                                                  **synth_kw(w))
-    c = coords.numpy().astype(np.int64) - start
     P = int(np.prod(ps))
-    pred = np.zeros((P,) + tuple(int(s) for s in size), np.float32)
-    pred[:, c[:, 0], c[:, 1], c[:, 2]] = patches.numpy().astype(np.float32).T
-    ni = np.zeros(tuple(int(s) for s in size), np.uint8)
-    ni[c[:, 0], c[:, 1], c[:, 2]] = numinst.numpy()
-    return pred, ni, start
+    vol = synth.neurites_3d(w['shape'], **synth_kw(w))
+    # the generator's own random sequence gives the first point of every polyline first
+    rng = np.random.default_rng(w['seed'])
+    out = []
+    starts = []
+    while len(out) < n:
+        p = np.array([rng.uniform(0, shape[0]), rng.uniform(0, shape[1]),
+                      rng.uniform(0, shape[2])])
+        rng.normal(size=3)
+        rng.uniform(0, 1)
+        start = np.clip(p.astype(int) - size // 2, 0, shape - size)
+        if any(np.all(np.abs(start - s0) < size) for s0 in starts):
+            continue                                        # overlapping an earlier region
+        lo, hi = int(start[0]), int(start[0] + size[0])
+        coords, patches, numinst = synth.neurite_rows(
+            w['shape'], ps, axis=0, lo=lo, hi=hi, device='cpu', box=(start, start + size),
+            volume=vol, **synth_kw(w))
+        if coords.shape[0] < 500:
+            continue
+        starts.append(start)
+        c = coords.numpy().astype(np.int64) - start
+        pred = np.zeros((P,) + tuple(int(s) for s in size), np.float32)
+        pred[:, c[:, 0], c[:, 1], c[:, 2]] = patches.numpy().astype(np.float32).T
+        ni = np.zeros(tuple(int(s) for s in size), np.uint8)
+        ni[c[:, 0], c[:, 1], c[:, 2]] = numinst.numpy()
+        out.append((pred, ni, start))
+    return out
+
+
+def sample_region(w):
+    return sample_regions(w, 1)[0]
 
 
 def cpu_reference_step(pred_np, numinst_np, ps, kw):
@@ -215,17 +235,21 @@ def run_reference_arm(args):
         return 0
     w = workload_from_args(args)
     cores = all_host_threads()
-    pred, ni, start = sample_region(w)
+    regions = sample_regions(w)
     times = []
     nfg = 0
     for i in range(args.warmup + args.steps):
-        nfg, dt, _ = cpu_reference_step(pred, ni, w['patchshape'], KW)
+        nfg, dt = 0, 0.0
+        for pred, ni, _ in regions:
+            n1, d1, _ = cpu_reference_step(pred, ni, w['patchshape'], KW)
+            nfg += n1
+            dt += d1
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     val = nfg / (ms * 1e-3) / 1e6
-    sample = 'region %s at %s of the volume (%d fg voxels), all stages, single block' % (
-        'x'.join(str(s) for s in pred.shape[1:]), tuple(int(v) for v in start), nfg)
+    sample = '%d regions of %s voxels of the volume (%d fg voxels), all stages, one block each' % (
+        len(regions), 'x'.join(str(s) for s in regions[0][0].shape[1:]), nfg)
     line = dict(metric='consensus+assembly fg Mvoxels/s', value=val, unit='Mvoxels/s',
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
                 higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32',
@@ -430,6 +454,7 @@ def main():
     ap.add_argument('--chunk', default=None, help='z,y,x chunksize')
     ap.add_argument('--workers', type=int, default=6)
     ap.add_argument('--mws', action='store_true')
+    ap.add_argument('--no-decoder', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
@@ -493,12 +518,14 @@ def main():
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
+    l0 = int(cc.call('ppp_launch_count'))
     t0.record()
     tw = time.perf_counter()
     for _ in range(steps):
         inst, info = device_step()
     t1.record()
     barrier()
+    launches_per_step = (int(cc.call('ppp_launch_count')) - l0) / steps
     wall_ms = (time.perf_counter() - tw) * 1e3 / steps
     ms = t0.elapsed_time(t1) / steps
     clocks = sampler.summary() if sampler else None
@@ -534,9 +561,9 @@ def main():
     # ---- per-call CUDA-event times: one extra single-stream pass --------------------
     with CallTimer(cc, torch) as ct:
         shard = sharded.RowShard(shape, axis, lo, hi, coords, patches, numinst)
-        sharded.stitch_shard(shard, slabs, workers=1, **kw)
+        sharded.stitch_shard(shard, slabs, workers=1, **dict(kw, ppp_pipeline=False,
+                                                            ppp_latency_stream=False))
     calls = ct.calls
-    n_calls = sum(d['calls'] for d in calls.values())
 
     # ---- digest of the whole label volume (equal for every N) ------------------------
     full = sharded.gather_slabs(inst, slabs, axis, shape)
@@ -559,9 +586,10 @@ def main():
         t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms = (float(x) for x in t.tolist())
-        c = torch.tensor([n_own, halo, h2d, d2h], device=dev, dtype=torch.int64)
+        c = torch.tensor([n_own, halo, h2d, d2h, int(launches_per_step)], device=dev,
+                         dtype=torch.int64)
         dist.all_reduce(c)
-        tot_fg, halo, h2d, d2h = (int(x) for x in c.tolist())
+        tot_fg, halo, h2d, d2h, launches_per_step = (int(x) for x in c.tolist())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -603,37 +631,78 @@ def main():
                  ms_per_step=e2e_ms, api='sharded.stitch_shard',
                  input='pinned host rows: coords i32 [G,3], patches f16 [G,343], numinst u8 [G]',
                  output='uint16 labels of the own slab, pinned host'),
-        gpu_launches=n_calls, clocks=clocks,
+        gpu_launches=launches_per_step, clocks=clocks,
         phase_ms={k: round(v, 2) for k, v in info['phase_ms'].items()},
         stage_ms={k: round(v['ms'], 3) for k, v in sorted(calls.items(), key=lambda kv: -kv[1]['ms'])},
     )
     if roofs:
         line['roofline'] = roofs[0]
         line['roofline_other'] = roofs[1:]
+    if world == 1 and not args.no_decoder:
+        # configs[3] (ppp+dec): the code -> patch decoder on the tensor cores for as many
+        # codes as the volume has foreground voxels, rows out (seeded weights and codes:
+        # no checkpoint ships with the reference)
+        try:
+            from patchperpix_b200.decoder import PatchDecoder, seeded_weights
+            dec = PatchDecoder(seeded_weights(), device=dev)
+            nb = 1 << 16
+            codes_d = torch.rand((nb, 176), device=dev)
+            for _ in range(2):
+                dec.decode_rows(codes_d)
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(1, min(40, tot_fg // nb))
+            d0.record()
+            for _ in range(reps):
+                dec.decode_rows(codes_d)
+            d1.record()
+            torch.cuda.synchronize()
+            dms = d0.elapsed_time(d1) / reps
+            flop = 2.0 * nb * 64 * 27 * (128 * 64 + 64 * 64 + 64 * 64)
+            tf_peak = 1607.7
+            pp = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+            if os.path.exists(pp):
+                tf_peak = float(json.load(open(pp)).get('bf16_tflops_sustained', tf_peak))
+            tf = flop / (dms * 1e-3) / 1e12
+            line.setdefault('roofline_other', []).append(dict(
+                bound='tensor', achieved=tf, peak=tf_peak, unit='TFLOP/s', frac=tf / tf_peak,
+                traffic=None, kernel='ppp_decode (tcgen05 implicit-GEMM decoder, configs[3])',
+                kernel_ms=dms, units=nb, mcodes_per_s=nb / dms / 1e3,
+                whole_volume_ms=dms * tot_fg / nb,
+                note='65 536 seeded codes per call, f16 rows out; flops = the three 3^3 '
+                     'tensor-core convolutions (128->64, 64->64, 64->64) per code'))
+        except Exception as e:
+            line.setdefault('roofline_other', []).append(dict(kernel='ppp_decode',
+                                                             failed=repr(e)))
     if not args.no_cpu_baseline and world == 1:
         try:
             cores = all_host_threads()
-            pred_s, ni_s, start = sample_region(w)
-            n_c, dt, inst_cpu = cpu_reference_step(pred_s, ni_s, tuple(int(p) for p in ps), KW)
-            # the same region through the CUDA path (rows form), labels must be identical
-            m = pred_s[P // 2] > np.float32(0.5)
-            c = np.argwhere(m)
-            v2r = torch.full(m.shape, -1, dtype=torch.int32)
-            v2r[c[:, 0], c[:, 1], c[:, 2]] = torch.arange(len(c), dtype=torch.int32)
-            rows = torch.from_numpy(np.ascontiguousarray(
-                pred_s[:, c[:, 0], c[:, 1], c[:, 2]].T.astype(np.float16)))
-            src = RowSource(rows.to(dev), v2r.to(dev))
-            fg_s = torch.from_numpy(m.astype(np.uint8)).to(dev)
-            inst_gpu, _ = vi.to_instance_seg(src, fg_s, fg_s.clone(), torch.from_numpy(ni_s).to(dev),
-                                             ps, **dict(KW, blockwise=False))
-            same = bool(np.array_equal(inst_gpu, inst_cpu))
+            n_c, dt, same, n_inst = 0, 0.0, True, 0
+            regions = sample_regions(w)
+            for pred_s, ni_s, start in regions:
+                n1, d1, inst_cpu = cpu_reference_step(pred_s, ni_s, tuple(int(p) for p in ps), KW)
+                n_c += n1
+                dt += d1
+                n_inst += int(inst_cpu.max())
+                # the same region through the CUDA path (rows form): identical labels
+                m = pred_s[P // 2] > np.float32(0.5)
+                c = np.argwhere(m)
+                v2r = torch.full(m.shape, -1, dtype=torch.int32)
+                v2r[c[:, 0], c[:, 1], c[:, 2]] = torch.arange(len(c), dtype=torch.int32)
+                rows = torch.from_numpy(np.ascontiguousarray(
+                    pred_s[:, c[:, 0], c[:, 1], c[:, 2]].T.astype(np.float16)))
+                src = RowSource(rows.to(dev), v2r.to(dev))
+                fg_s = torch.from_numpy(m.astype(np.uint8)).to(dev)
+                inst_gpu, _ = vi.to_instance_seg(src, fg_s, fg_s.clone(),
+                                                 torch.from_numpy(ni_s).to(dev), ps,
+                                                 **dict(KW, blockwise=False))
+                same = same and bool(np.array_equal(inst_gpu, inst_cpu))
             line['parity_checked'] = same
             line['cpu_baseline'] = dict(
                 value=n_c / dt / 1e6, unit='Mvoxels/s', cores=cores, kind='reference',
-                sample='region %s at %s of the volume (%d fg voxels, %d instances), all stages, '
-                       'single block, %.1f s; GPU labels on the same region identical: %s' % (
-                           'x'.join(str(s) for s in m.shape), tuple(int(v) for v in start), n_c,
-                           int(inst_cpu.max()), dt, same))
+                sample='%d regions of %s voxels of the volume (%d fg voxels, %d instances), all '
+                       'stages, one block each, %.1f s; GPU labels on the same regions '
+                       'identical: %s' % (len(regions), 'x'.join(str(v) for v in CPU_SAMPLE), n_c,
+                                          n_inst, dt, same))
             if not same:
                 raise AssertionError('GPU labels differ from the CPU reference arm on the sample')
         except AssertionError:

@@ -74,6 +74,9 @@ typedef struct ppp_cfg {
 
 const char* ppp_last_error(void);
 int ppp_version(void);
+/* kernels launched by this library since it was loaded (own kernels + the CUB kernels
+ * compiled into it), counted at the runtime's launch entry. */
+int64_t ppp_launch_count(void);
 
 /* ---- step 0: gate + compaction (vote_instances.py:276-287 does this on the
  * host with np.where + a python list comprehension) ------------------------ */

@@ -52,8 +52,10 @@ def build(force=False, verbose=False):
         with open(os.path.join(BUILD, src[:-3] + '.ptxas.log'), 'w') as f:
             f.write(out)
     if relink:
-        cmd = [_nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a',
-               '-o', SO] + objs + ['-lcudart']
+        # shared runtime + -Bsymbolic: the launch counter in ppp_api.cu interposes
+        # cudaLaunchKernel for this library only
+        cmd = [_nvcc(), '-shared', '--cudart', 'shared', '-Xlinker', '-Bsymbolic', '-gencode',
+               'arch=compute_100a,code=sm_100a', '-o', SO] + objs + ['-lcudart', '-ldl']
         subprocess.run(cmd, check=True)
     return SO
 

@@ -104,6 +104,7 @@ _lib = None
 _SIGS = {
     'ppp_last_error': (ctypes.c_char_p, []),
     'ppp_version': (ctypes.c_int, []),
+    'ppp_launch_count': (ctypes.c_int64, []),
     'ppp_gate': (ctypes.c_int, ['p', 'p', 'p', 'cfg', 'p', 'p']),
     'ppp_compact_scratch_bytes': (ctypes.c_int64, ['i64']),
     'ppp_compact': (ctypes.c_int, ['p', 'i64', 'p', 'p', 'p', 'p', 'p']),

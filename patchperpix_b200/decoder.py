@@ -42,6 +42,23 @@ def _fold_upsample_conv(w):
     return out.astype(np.float16)
 
 
+def seeded_weights(seed=0, gain=2.5):
+    """seeded weights with the flylight decoder's layer shapes (no checkpoint ships with
+    the reference; timing and plumbing tests only)."""
+    rng = np.random.default_rng(seed)
+
+    def conv(cout, cin, k):
+        b = 1.0 / np.sqrt(cin * k ** 3)
+        return (rng.uniform(-b, b, (cout, cin, k, k, k)).astype(np.float32) * gain,
+                rng.uniform(-b, b, (cout,)).astype(np.float32))
+    W = {}
+    for name, (co, ci, k) in dict(from_code=(128, 22, 1), up0=(64, 128, 3), conv0a=(64, 64, 3),
+                                  conv0b=(64, 64, 3), up1=(1, 64, 3), conv1a=(1, 1, 3),
+                                  conv1b=(1, 1, 3)).items():
+        W[name + '.w'], W[name + '.b'] = conv(co, ci, k)
+    return W
+
+
 class PatchDecoder:
     """weights: dict with the keys of oracle.decoder_torch.make_weights /
     the decoder part of the reference checkpoint (`model.decoder`)."""
@@ -82,6 +99,22 @@ class PatchDecoder:
                 cc.ptr(self.w_c1a), cc.ptr(self.b_c1a), cc.ptr(self.w_c1b), cc.ptr(self.b_c1b),
                 1 if sigmoid else 0, cc.ptr(out), cc.ptr(scratch), cc.current_stream_ptr())
         return out[:B]
+
+    def decode_rows(self, codes, batch=1 << 16):
+        """the codes of the stored voxels [G,176] -> compact patch ROWS f16 [G,343]
+        (sigmoid applied), the input form of the rows path (assembly.RowSource,
+        sharded.RowShard): decode.py:39-65 scatters the decoded patches into a dense
+        [P,Z,Y,X] array and stores it as float16; here the rows stay rows and the
+        dense array never exists.  The reference stores float16 LOGITS and applies
+        expit after loading (utilVoteInstances.py:249-250); storing the float16
+        PROBABILITY differs from that by at most 2.5e-4 (half an ulp below 1), inside
+        the 1e-3 tolerance stated for decoded patches."""
+        import torch
+        G = int(codes.shape[0])
+        out = torch.empty((G, 343), dtype=torch.float16, device=self.dev)
+        for s0 in range(0, G, batch):
+            out[s0:s0 + batch] = self.decode(codes[s0:s0 + batch], sigmoid=True)
+        return out
 
     def decode_volume(self, pred_code, fg, sigmoid=True):
         """decode_sample (decode.py:16-65): codes [176,Z,Y,X] + fg mask ->

@@ -28,6 +28,7 @@ lives and who does what:
 Labels are identical for every world size (tests/test_sharded.py; bench.py checks
 a digest) and equal to the dense single-process driver (stitch_arrays).
 """
+import concurrent.futures
 import logging
 import threading
 
@@ -510,43 +511,33 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
 
     # ---- phase 1: the blocks of my slab ----------------------------------------------
     my_blocks = [b for b in range(nblk) if owner[b] == rank]
-    res = _run_jobs(my_blocks, lambda b: _block_job(shard, offsets[b], chunksize, ps, kwargs, block_fn),
-                    workers)
-    mine = {b: r for b, r in zip(my_blocks, res) if r is not None}
-    lap('blocks')
-    blocks = _allgather_edges(mine, nblk, lambda b: owner[b])       # exchange (1)
-    lap('allgather_block_edges')
-    selected = {}
-
-    # ---- phase 2: face jobs, on the owner of the higher block ------------------------
+    mine, box, selected = {}, {}, {}
     key_of = {tuple(int(v) for v in o): i for i, o in enumerate(offsets)}
-    jobs = []
-    first_nonempty = next((b for b in range(nblk) if b in blocks), None)
-    for b in range(nblk):
-        if b not in blocks or b == first_nonempty:
-            continue                                             # :151-156, :178-181
-        for dim in range(3):                                     # -z, -y, -x (:125-128)
-            nb_off = offsets[b].copy()
-            nb_off[dim] -= chunksize[dim]
-            nb = key_of.get(tuple(int(v) for v in nb_off))
-            if nb is None or nb >= b or nb not in blocks:
-                continue
-            jobs.append((b, nb, dim))
 
     def selected_of(b):
         """the selected patches of a block = the nodes of its pair list (:166-171);
         computed where first needed, from any thread (a race only repeats the work)"""
         got = selected.get(b)
         if got is None:
-            p = blocks[b][0].reshape(-1, 3).astype(np.int64)
+            src = mine[b] if b in mine else box['blocks'][b]
+            p = src[0].reshape(-1, 3).astype(np.int64)
             key = (p[:, 0] * shape[1] + p[:, 1]) * shape[2] + p[:, 2]
             _, first = np.unique(key, return_index=True)     # sorted by (z,y,x) like
             got = selected[b] = p[first]                     # np.unique(axis=0)
         return got
 
-    def face_host(j):
-        """candidates and cross pairs of face job j (host: KD tree, set order)"""
-        b, nb, dim = jobs[j]
+    def neighbours(b, sign):
+        for dim in range(3):                                     # -z, -y, -x (:125-128)
+            nb_off = offsets[b].copy()
+            nb_off[dim] += sign * chunksize[dim]
+            nb = key_of.get(tuple(int(v) for v in nb_off))
+            if nb is not None and (nb < b if sign < 0 else nb > b):
+                yield nb, dim
+
+    def face_host(bnd):
+        """candidates and cross pairs of the face (block, neighbour, axis) (host: KD
+        tree, set order); None if there is nothing to pair"""
+        b, nb, dim = bnd
         cur, nbc = face_candidates(selected_of(b), selected_of(nb), offsets[b], dim, ps)
         if len(cur) == 0 or len(nbc) == 0:
             return None
@@ -555,8 +546,80 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
             return None
         return cands, pa
 
+    batch_faces = block_fn is None and kwargs.get('ppp_batch_faces', True)
+    early = {}                  # face (block, lower neighbour, axis) -> future of face_host
+    finished = set()
+    hpool = concurrent.futures.ThreadPoolExecutor(max_workers=3) if batch_faces else None
+
+    def block_done(b, r):
+        """the host part of a face between two of my blocks starts as soon as both are
+        assembled, on a small thread pool, while the GPU works on the other blocks"""
+        finished.add(b)
+        if r is None:
+            return
+        mine[b] = r
+        if hpool is None:
+            return
+        for nb, dim in neighbours(b, -1):
+            if nb in mine:
+                early[(b, nb, dim)] = hpool.submit(face_host, (b, nb, dim))
+        for nb, dim in neighbours(b, +1):
+            if nb in mine:
+                early[(nb, b, dim)] = hpool.submit(face_host, (nb, b, dim))
+
+    if block_fn is None and shard.dev.type == 'cuda' and kwargs.get('ppp_pipeline', True) and \
+            not isinstance(kwargs.get('score_threshold', False), float):
+        # one host thread, many blocks in flight (pipeline.py)
+        from . import pipeline
+        margin = ps // 2
+        ckw = {k: v for k, v in kwargs.items() if k != 'patchshape'}
+
+        def steps(b, pool):
+            off = np.asarray(offsets[b])
+            src, fg, mask, numinst, start = shard.region(off - margin, off + chunksize + margin,
+                                                         **kwargs)
+            got = yield from pipeline.block_steps(src, fg, mask, numinst, ps, pool, **ckw)
+            if got is None:
+                return None
+            pairs = got[0].astype(np.int64) + np.tile(start, 2)      # :650 and :162
+            return pairs.astype(np.uint32), got[1]
+        pipeline.run_blocks(my_blocks, steps, max_inflight=int(kwargs.get('ppp_inflight', 16)),
+                            on_done=block_done)
+    else:
+        res = _run_jobs(my_blocks,
+                        lambda b: _block_job(shard, offsets[b], chunksize, ps, kwargs, block_fn),
+                        workers)
+        for b, r in zip(my_blocks, res):
+            block_done(b, r)
+    lap('blocks')
+    # exchange (1) runs on a helper thread: this rank finishes the host part of its
+    # interior faces while the slower ranks finish their blocks
+    def exchange1():
+        if shard.dev.type == 'cuda':
+            torch.cuda.set_device(shard.dev)
+        box['blocks'] = _allgather_edges(mine, nblk, lambda b: owner[b])
+    ex = threading.Thread(target=exchange1)
+    ex.start()
+    early_res = {k: f.result() for k, f in early.items()}
+    if hpool is not None:
+        hpool.shutdown()
+    lap('faces_host_early')
+    ex.join()
+    blocks = box['blocks']
+    lap('allgather_block_edges')
+
+    # ---- phase 2: face jobs, on the owner of the higher block ------------------------
+    jobs = []
+    first_nonempty = next((b for b in range(nblk) if b in blocks), None)
+    for b in range(nblk):
+        if b not in blocks or b == first_nonempty:
+            continue                                             # :151-156, :178-181
+        for nb, dim in neighbours(b, -1):
+            if nb in blocks:
+                jobs.append((b, nb, dim))
+
     def face(j):
-        cp = face_host(j)
+        cp = face_host(jobs[j])
         if cp is None:
             return None
         return _face_job(shard, cp[0], cp[1], ps, kwargs, block_fn)
@@ -568,7 +631,9 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
         # face job reads does not depend on the extent of its region (every centre that can
         # vote on them lies inside: the region is padded by patchshape + patchshape//2,
         # :261-278), so one gate/prepare/consensus/patch-graph pass over the row serves them all
-        host = _run_jobs(my_jobs, face_host, workers)
+        late = [j for j in my_jobs if jobs[j] not in early_res]
+        late_res = dict(zip(late, _run_jobs([jobs[j] for j in late], face_host, workers)))
+        host = [early_res[jobs[j]] if jobs[j] in early_res else late_res[j] for j in my_jobs]
         lap('faces_host')
         groups = {}
         for j, cp in zip(my_jobs, host):

@@ -45,3 +45,43 @@ def test_decode_volume_scatters_foreground_only():
     assert float(vol[:, ~fg].abs().max()) == 0.0
     ref = torch.sigmoid(dt.decode_ref(code.reshape(176, -1).T[fg.reshape(-1)], W))
     assert float((vol[:, fg].T - ref).abs().max()) <= 1e-3
+
+
+@pytest.mark.gpu
+def test_decode_rows_feed_the_rows_path():
+    """configs[3] in small: codes of the foreground voxels -> f16 patch rows -> blockwise
+    assembly, no dense [P,Z,Y,X] array anywhere; equals the dense route
+    (decode_volume -> float16 -> to_instance_seg)."""
+    import torch
+    from patchperpix_b200.decoder import PatchDecoder
+    from patchperpix_b200.assembly import RowSource
+    from patchperpix_b200 import vote_instances as vi
+    from oracle import decoder_torch
+    W = decoder_torch.make_weights(seed=3)
+    dec = PatchDecoder(W)
+    rng = np.random.default_rng(0)
+    shape = (14, 24, 24)
+    fg = rng.random(shape) < 0.12
+    fg[:3] = fg[-3:] = False
+    fg[:, :3] = fg[:, -3:] = False
+    fg[:, :, :3] = fg[:, :, -3:] = False
+    c = np.argwhere(fg)
+    codes = torch.from_numpy(rng.random((len(c), 176)).astype(np.float32)).cuda()
+    rows = dec.decode_rows(codes)
+    assert rows.dtype == torch.float16 and rows.shape == (len(c), 343)
+    ref = dec.decode(codes, sigmoid=True)
+    assert float((rows.float() - ref).abs().max()) <= 2.5e-4
+    v2r = torch.full(shape, -1, dtype=torch.int32)
+    v2r[c[:, 0], c[:, 1], c[:, 2]] = torch.arange(len(c), dtype=torch.int32)
+    src = RowSource(rows, v2r.cuda())
+    kw = dict(patch_threshold=0.5, fc_threshold=0.5, cuda=True, blockwise=False,
+              select_patches_for_sparse_data=True, includeSinglePatchCCS=True, mws=False,
+              consensus_norm_prob_product=True, consensus_prob_product=True,
+              consensus_norm_aff=True, consensus_interleaved_cnt=False,
+              vi_bg_use_inv_th=False, vi_bg_use_half_th=False, vi_bg_use_less_than_th=True,
+              rank_norm_patch_score=True, rank_int_counter=False, patch_graph_norm_aff=True,
+              overlapping_inst=False)
+    fgt = torch.from_numpy(fg.astype(np.uint8)).cuda()
+    a, _ = vi.to_instance_seg(src, fgt, fgt.clone(), fgt.clone(), np.array([7, 7, 7]), **kw)
+    b, _ = vi.to_instance_seg(src.dense(), fgt, fgt.clone(), fgt.clone(), np.array([7, 7, 7]), **kw)
+    assert np.array_equal(a, b)

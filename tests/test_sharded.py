@@ -193,9 +193,11 @@ def test_sharded_cuda_matches_reference_golden(mws):
     g, kw, pred, numinst = _load()
     want = np.load(os.path.join(gu.GOLD, 'mws_cases.npz'))['blockwise_inst'] if mws \
         else g['instances']
-    for workers in (1, 3):
-        inst, info, _, _ = _run_rank(pred, numinst, dict(kw, mws=mws), 0, 1, hooks=False,
-                                     device='cuda', workers=workers)
+    # blocks through the single-thread pipeline (pipeline.py, the default) and through
+    # host threads calling to_instance_seg; face jobs batched per block row and one by one
+    for workers, extra in ((1, {}), (3, dict(ppp_pipeline=False, ppp_batch_faces=False))):
+        inst, info, _, _ = _run_rank(pred, numinst, dict(kw, mws=mws, **extra), 0, 1,
+                                     hooks=False, device='cuda', workers=workers)
         assert np.array_equal(inst.cpu().numpy().astype(np.uint16), want)
 
 

@@ -9,20 +9,7 @@ import numpy as np
 from patchperpix_b200.decoder import PatchDecoder
 
 
-def random_weights(seed=0, gain=2.5):
-    """seeded weights with the decoder's layer shapes (values do not matter for timing)."""
-    rng = np.random.default_rng(seed)
-
-    def conv(cout, cin, k):
-        b = 1.0 / np.sqrt(cin * k ** 3)
-        return (rng.uniform(-b, b, (cout, cin, k, k, k)).astype(np.float32) * gain,
-                rng.uniform(-b, b, (cout,)).astype(np.float32))
-    W = {}
-    for name, (co, ci, k) in dict(from_code=(128, 22, 1), up0=(64, 128, 3), conv0a=(64, 64, 3),
-                                  conv0b=(64, 64, 3), up1=(1, 64, 3), conv1a=(1, 1, 3),
-                                  conv1b=(1, 1, 3)).items():
-        W[name + '.w'], W[name + '.b'] = conv(co, ci, k)
-    return W
+from patchperpix_b200.decoder import seeded_weights as random_weights  # noqa: E402
 
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
