@@ -140,6 +140,13 @@ int ppp_consensus_small(const float* rv, const uint16_t* rb16, const uint8_t* fl
                         const uint8_t* need, int64_t F, const ppp_cfg* cfg,
                         float* cons, uint32_t* cnt, void* stream);
 
+/* need[row] = 1 for every row whose voxel lies within (hz,hy,hx) of one of the m
+ * centres (i32 [m][3], block coordinates); need u8 [F] zeroed by the caller.  Builds the
+ * `need` masks above from the candidate patches of face jobs. */
+int ppp_mark_windows(const int32_t* centres, int64_t m, const ppp_cfg* cfg,
+                     int32_t hz, int32_t hy, int32_t hx, const int32_t* fgidx,
+                     uint8_t* need, void* stream);
+
 /* ---- step 2: rank (rankPatches.cu) ----------------------------------------
  * score f32 [Z][Y][X]: border voxels -1 / -9999999, non-fg interior 0. */
 int64_t ppp_rank_scratch_bytes(const ppp_cfg* cfg, int64_t F);

@@ -247,6 +247,16 @@ class BlockAssembler:
         self._prepared = True
         return self.F
 
+    def window_rows(self, centres, half):
+        """u8 [F]: 1 for the rows whose voxel lies within `half` (per axis) of one of the
+        `centres` (i32 [m,3] device tensor, block coordinates)."""
+        torch = _torch()
+        need = torch.zeros(max(self.F, 1), dtype=torch.uint8, device=self.dev)
+        cc.call('ppp_mark_windows', cc.ptr(centres.contiguous()), int(centres.shape[0]), self.cfg,
+                int(half[0]), int(half[1]), int(half[2]), cc.ptr(self.fgidx), cc.ptr(need),
+                self.stream)
+        return need
+
     def received(self, need=None):
         """the "received" tables of the small-window consensus (ppp_received); need: u8
         [F], rows with 0 are skipped (must cover the wanted rows and their partners)."""

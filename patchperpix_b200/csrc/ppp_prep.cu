@@ -476,3 +476,35 @@ extern "C" int ppp_received_rows(const uint16_t* patches, const int32_t* vox2row
         (int)ppp_received_row_words(cfg));
     return ppp_check("ppp_received_rows");
 }
+
+// ---------------------------------------------------------------------------
+// row masks for partial consensus runs (face jobs of the blockwise stitcher only
+// read the rows inside the windows of their candidate patches): need[row] = 1 for
+// every row whose voxel lies within (hz,hy,hx) of one of the m centres.  One CTA
+// per centre; need must be zeroed by the caller.
+// ---------------------------------------------------------------------------
+__global__ void mark_windows_kernel(const int32_t* __restrict__ centres, ppp_cfg cfg,
+                                    int hz, int hy, int hx,
+                                    const int32_t* __restrict__ fgidx, uint8_t* __restrict__ need)
+{
+    Geo g = make_geo(cfg);
+    const int cz = centres[3 * blockIdx.x], cy = centres[3 * blockIdx.x + 1],
+              cx = centres[3 * blockIdx.x + 2];
+    const int ny = 2 * hy + 1, nx = 2 * hx + 1, n = (2 * hz + 1) * ny * nx;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int z = cz - hz + i / (ny * nx), y = cy - hy + (i / nx) % ny, x = cx - hx + i % nx;
+        if (z < 0 || z >= g.Z || y < 0 || y >= g.Y || x < 0 || x >= g.X) continue;
+        const int r = fgidx[((int64_t)z * g.Y + y) * g.X + x];
+        if (r >= 0) need[r] = 1;
+    }
+}
+
+extern "C" int ppp_mark_windows(const int32_t* centres, int64_t m, const ppp_cfg* cfg,
+                                int32_t hz, int32_t hy, int32_t hx, const int32_t* fgidx,
+                                uint8_t* need, void* stream)
+{
+    if (m <= 0) return 0;
+    mark_windows_kernel<<<(unsigned)m, 128, 0, (cudaStream_t)stream>>>(centres, *cfg, hz, hy, hx,
+                                                                      fgidx, need);
+    return ppp_check("ppp_mark_windows");
+}

@@ -133,6 +133,7 @@ _SIGS = {
     'ppp_received': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
     'ppp_received_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
     'ppp_consensus_small': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),
+    'ppp_mark_windows': (ctypes.c_int, ['p', 'i64', 'cfg', 'i32', 'i32', 'i32', 'p', 'p', 'p']),
     'ppp_gate_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'cfg', 'p', 'p']),
     'ppp_prepare_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p', 'p', 'p']),
     'ppp_patch_graph_rows': (ctypes.c_int, ['p', 'p', 'p', 'p', 'p', 'p', 'p', 'i64', 'cfg', 'p', 'p', 'p']),

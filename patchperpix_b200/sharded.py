@@ -259,18 +259,6 @@ def _face_job(shard, candidates, pa, ps, kwargs, block_fn=None):
     return overlapping.astype(np.uint32), np.asarray(aff, np.float32)
 
 
-def _box_dilate(vol, size):
-    """dilation of a [1,1,Z,Y,X] indicator by a box of odd `size`, one axis at a time"""
-    import torch
-    for ax in range(3):
-        k = [1, 1, 1]
-        k[ax] = size[ax]
-        if size[ax] > 1:
-            vol = torch.nn.functional.max_pool3d(vol, kernel_size=tuple(k), stride=1,
-                                                 padding=tuple(v // 2 for v in k))
-    return vol
-
-
 def _face_batch(shard, faces, ps, kwargs):
     """the face jobs `faces` = [(job, (candidates, pair index array))] as ONE pass over
     the bounding box of their regions.  Returns {job: (pairs u32 [n,6] volume coordinates,
@@ -305,15 +293,10 @@ def _face_batch(shard, faces, ps, kwargs):
     org = np.concatenate([np.broadcast_to(p[5] - b_start, (int(p[2].sum()), 3)) for p in per])
     cen = np.concatenate([p[4] for p in per]) - b_start
     ok = np.all((cen >= 0) & (cen < np.asarray(bshape)), axis=1)
-    cen = torch.from_numpy(cen[ok]).to(dev)
-    seed = torch.zeros((1, 1) + bshape, dtype=torch.float32, device=dev)
-    seed[0, 0, cen[:, 0], cen[:, 1], cen[:, 2]] = 1.0
-    win = _box_dilate(seed, [int(p) for p in ps])
-    rv_l = asm.rowvox.long()
-    need = win.reshape(-1)[rv_l].to(torch.uint8).contiguous()
-    # their partners (anything within 2*ps-1) must have tables too
-    win2 = _box_dilate(win, [int(2 * p - 1) for p in ps])
-    asm.received(win2.reshape(-1)[rv_l].to(torch.uint8).contiguous())
+    cen = torch.from_numpy(np.ascontiguousarray(cen[ok].astype(np.int32))).to(dev)
+    need = asm.window_rows(cen, margin)
+    # their partners (anything within 2*ps-1 of a wanted row) must have tables too
+    asm.received(asm.window_rows(cen, margin + ps - 1))
     asm.consensus(need=need)
     aff_all = np.zeros(0, np.float32)
     if len(pk):
@@ -670,8 +653,9 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
     inst = torch.zeros(own_box, dtype=torch.int32, device=shard.dev)
     if not plist:
         return inst, info
-    pairs = np.concatenate(plist).astype(np.uint32)
-    aff = np.concatenate(alist).astype(np.float32)
+    pairs = np.concatenate(plist)
+    aff = np.concatenate(alist)
+    assert pairs.dtype == np.uint32 and aff.dtype == np.float32
     info['pairs'] = pairs
     info['aff'] = aff
 

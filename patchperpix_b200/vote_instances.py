@@ -154,19 +154,9 @@ def to_instance_seg(pred_affs, foreground, mask_to_cover, numinst, patchshape,
                 and kwargs.get('selected_patch_pairs') is not None and asm.small:
             # stitcher's face job (stitch_patch_graph.py:323-328): only the patch graph of the
             # given pairs reads the consensus, i.e. rows inside the windows of those patches
-            sc = torch.from_numpy(np.asarray(kwargs['selected_patches'],
-                                             dtype=np.int64).reshape(-1, 3)).to(asm.dev)
-            ok = ((sc >= 0) & (sc < torch.tensor(shape, device=asm.dev))).all(dim=1)
-            sc = sc[ok]
-            seed = torch.zeros((1, 1) + shape, dtype=torch.float32, device=asm.dev)
-            seed[0, 0, sc[:, 0], sc[:, 1], sc[:, 2]] = 1.0
-            win = seed
-            for ax in range(3):                      # box dilation, one axis at a time
-                k = [1, 1, 1]
-                k[ax] = int(patchshape[ax])
-                win = torch.nn.functional.max_pool3d(win, kernel_size=tuple(k), stride=1,
-                                                     padding=tuple(v // 2 for v in k))
-            need = win.reshape(-1)[asm.rowvox.long()].to(torch.uint8).contiguous()
+            sc = np.asarray(kwargs['selected_patches'], dtype=np.int64).reshape(-1, 3)
+            sc = sc[np.all((sc >= 0) & (sc < np.asarray(shape)), axis=1)]
+            need = asm.window_rows(torch.from_numpy(sc.astype(np.int32)).to(asm.dev), rad)
         asm.consensus(need=need)
     if kwargs.get('save_consensus', False):
         return None, None
