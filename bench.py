@@ -601,14 +601,20 @@ def main():
     # rank = patch + K consensus values + 1 score
     bytes_unit = dict(ppp_consensus=P * 2 + 1 + K * 8, ppp_rank=P * 2 + K * 4 + 4)
     step_ms_profiled = sum(d['ms'] for d in calls.values())
+    # DRAM bytes per row of the same kernels from the committed ncu --set full capture
+    traffic = {}
+    tp = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
     roofs = []
     for name in ('ppp_consensus', 'ppp_rank'):
         d = calls.get(name)
         if not d or d['ms'] <= 0:
             continue
         ach = bytes_unit[name] * d['units'] / (d['ms'] * 1e-3) / 1e9
+        tr = traffic.get(name, {}).get('dram_bytes_per_row')
         roofs.append(dict(bound='hbm', achieved=ach, peak=peak, unit='GB/s', frac=ach / peak,
-                          traffic=None, kernel=name, kernel_ms=d['ms'], launches=d['calls'],
+                          traffic=(tr * d['units'] / d['calls']) if tr else None, kernel=name, kernel_ms=d['ms'], launches=d['calls'],
                           units=d['units'], bytes_per_fg_voxel=bytes_unit[name],
                           share_of_gpu_time=d['ms'] / step_ms_profiled, peak_source=how,
                           note='summed over the %d calls of one step (blocks + face regions); '

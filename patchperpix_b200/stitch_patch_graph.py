@@ -406,8 +406,7 @@ def paint_global(inputs, pairs, aff, rank=0, world=1, **kwargs):
             zi, yi, xi = (torch.from_numpy(a).to(dev) for a in (z, y, x))
             pt = inputs.device_pred[:, zi, yi, xi].T.float().contiguous()
         else:
-            patches = np.ascontiguousarray(np.asarray(inputs.pred)[:, z, y, x].T.astype(np.float32))
-            pt = torch.from_numpy(patches).to(dev)
+            pt = torch.from_numpy(gather_patches(inputs.pred, z, y, x)).to(dev)
         cc.call('ppp_paint_patches', cc.ptr(pt), cc.ptr(nd), len(nodes), cc.ptr(comp), cfg,
                 cc.ptr(inst), stream)
     dist = _dist()
@@ -448,6 +447,27 @@ def finish_outputs(instances, foreground, **kwargs):
         dil = pp.dilate_instances(inst)
         out[res_key + '_dil_1'] = u16(dil)
         out[res_key + '_masked_dil_1'] = u16(torch.where(fg, dil, torch.zeros_like(dil)))
+    return out
+
+
+def gather_patches(pred, z, y, x, tile=64):
+    """pred[:, z, y, x].T as float32 [n,P] without loading the volume: the nodes are
+    grouped by tile and one box per tile is read (the reference reads node by node when
+    the prediction is larger than 20 GB, stitch_patch_graph.py:367-385)."""
+    n = len(z)
+    out = np.zeros((n, int(pred.shape[0])), np.float32)
+    if n == 0:
+        return out
+    if isinstance(pred, np.ndarray) and not isinstance(pred, np.memmap):
+        return np.ascontiguousarray(pred[:, z, y, x].T.astype(np.float32))
+    key = (z // tile) * 1000003 + (y // tile) * 1009 + (x // tile)
+    order = np.argsort(key, kind='stable')
+    bounds = np.flatnonzero(np.diff(key[order])) + 1
+    for idx in np.split(order, bounds):
+        z0, y0, x0 = z[idx].min(), y[idx].min(), x[idx].min()
+        box = np.asarray(pred[:, int(z0):int(z[idx].max()) + 1, int(y0):int(y[idx].max()) + 1,
+                              int(x0):int(x[idx].max()) + 1])
+        out[idx] = box[:, z[idx] - z0, y[idx] - y0, x[idx] - x0].T
     return out
 
 

@@ -320,3 +320,35 @@ def test_score_threshold_cuts_the_cover():
         assert np.array_equal(inst, ref), thr
         hit = hit or not np.array_equal(ref, base)
     assert hit, "thresholds too low to change anything: the test would be vacuous"
+
+
+def test_gather_patches_reads_boxes_not_the_volume(tmp_path):
+    """stitch_patch_graph.py:367-385: node patches of a prediction that stays on disk."""
+    rng = np.random.default_rng(3)
+    a = rng.random((27, 20, 70, 90)).astype(np.float16)
+    g = io_util.ZarrLiteGroup(str(tmp_path / 'p.zarr'), 'w')
+    g.create_dataset('volumes/pred_affs', data=a, chunks=(27, 8, 32, 32))
+    arr = io_util.open_zarr(str(tmp_path / 'p.zarr'))['volumes/pred_affs']
+    z, y, x = rng.integers(0, 20, 300), rng.integers(0, 70, 300), rng.integers(0, 90, 300)
+    got = spg.gather_patches(arr, z, y, x, tile=16)
+    assert np.array_equal(got, a[:, z, y, x].T.astype(np.float32))
+    assert np.array_equal(spg.gather_patches(a, z, y, x), got)
+
+
+def test_pair_order_fallback_without_the_set_replay(monkeypatch):
+    """aff_patch_graph.py:57-110 enumerates a python SET; ppp_pyset_order replays CPython's
+    table, and if its self-check ever fails (another interpreter) the plain python path
+    must give the same pairs in the same order."""
+    import scipy.spatial
+    from patchperpix_b200 import assembly
+    rng = np.random.default_rng(5)
+    pts = np.unique(rng.integers(0, 40, (400, 3)), axis=0).astype(np.uint32)
+    tree = scipy.spatial.cKDTree(pts, leafsize=4)
+    thr = np.array([14.0, 14.0, 14.0])
+    assert assembly._pyset_replay_ok()
+    fast = assembly.query_pairs_filtered(tree, pts, 42, thr)
+    fast2 = assembly.query_pairs_set_order(tree, 42)
+    monkeypatch.setattr(assembly, '_PYSET_REPLAY', False)
+    slow = assembly.query_pairs_filtered(tree, pts, 42, thr)
+    slow2 = assembly.query_pairs_set_order(tree, 42)
+    assert len(fast) > 100 and np.array_equal(fast, slow) and np.array_equal(fast2, slow2)

@@ -33,8 +33,19 @@ def main():
     shard = sharded.RowShard(shape, 0, 0, shape[0], c, p, ni)
     shard.exchange_halo([(0, shape[0])], 0)
     kw = dict(bench.KW, patchshape=list(w['patchshape']))
+    if os.environ.get('PPP_TUNE'):
+        kw['ppp_tune'] = int(os.environ['PPP_TUNE'], 0)
     src, fg, mask, numinst, _ = shard.region(np.zeros(3, int), np.array(shape), **kw)
     print('rows', int(c.shape[0]))
+    if os.environ.get('PPP_STAGES'):
+        from patchperpix_b200 import cuda_code as cc
+        kw['ppp_latency_stream'] = False
+        vi.do_block(src, fg, mask, numinst, return_intermediates=True, **kw)
+        with bench.CallTimer(cc, torch) as ct:
+            for i in range(3):
+                vi.do_block(src, fg, mask, numinst, return_intermediates=True, **kw)
+        print('tune', kw.get('ppp_tune', 0), {k: round(v['ms'] / 3, 3) for k, v in ct.calls.items()})
+        return
     if os.environ.get('PPP_CPROFILE'):
         import cProfile
         import pstats
