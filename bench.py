@@ -455,6 +455,7 @@ def main():
     ap.add_argument('--workers', type=int, default=6)
     ap.add_argument('--mws', action='store_true')
     ap.add_argument('--no-decoder', action='store_true')
+    ap.add_argument('--no-c2', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
@@ -478,6 +479,9 @@ def main():
     ps = np.array(w['patchshape'])
     _, P, _, _, _, K = patch_geometry(ps)
     kw = dict(KW, patchshape=list(w['patchshape']), chunksize=list(w['chunksize']), mws=args.mws)
+    for k in ('PPP_INFLIGHT', 'PPP_STREAMS'):            # tuning experiments
+        if os.environ.get(k):
+            kw[k.lower()] = int(os.environ[k])
     shape = w['shape']
 
     # ---- inputs: the patch rows of my slab, resident in HBM ---------------------
@@ -679,6 +683,66 @@ def main():
         except Exception as e:
             line.setdefault('roofline_other', []).append(dict(kernel='ppp_decode',
                                                              failed=repr(e)))
+    if world == 1 and not args.no_c2:
+        # BASELINE configs[1] (round 1's workload), kept as a side leg: one 2-D image
+        # 696x520, patchshape 1x41x41, dense float32 input, single block
+        try:
+            from patchperpix_b200.assembly import BlockAssembler
+            ps2 = np.array([1, 41, 41])
+            _, P2, _, _, _, K2 = patch_geometry(ps2)
+            lab2, ni2 = synth.worms_2d((520, 696), n_worms=40, seed=2)
+            pred2 = synth.patches_from_labels(lab2, ps2, seed=2, device=dev)
+            fg2 = (pred2[P2 // 2] > 0.5).to(torch.uint8)
+            ov2 = torch.from_numpy((ni2 > 1).astype(np.uint8)).to(dev)
+            mask2 = fg2.clone()
+            mask2[ov2 > 0] = 0
+            kw2 = dict(KW, blockwise=False)
+            n2 = int(fg2.sum().item())
+
+            def c2_step(ev=None):
+                asm = BlockAssembler(pred2, fg2, ov2, ps2, **kw2)
+                asm.prepare()
+                if ev:
+                    ev[0].record()
+                asm.consensus(want_cnt=True)
+                if ev:
+                    ev[1].record()
+                asm.rank()
+                if ev:
+                    ev[2].record()
+                order = asm.ranked()
+                sel = asm.thin(mask2, asm.cover(mask2, order))
+                pairs = asm.patch_pairs(asm.coords(sel))
+                pd = torch.from_numpy(pairs.view(np.int32)).to(dev)
+                inst2, _ = asm.label(pd, asm.patch_graph(pd), sel)
+                return inst2
+            for _ in range(3):
+                c2_step()
+            reps = 8
+            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(reps)]
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            c0.record()
+            for i in range(reps):
+                c2_step(evs[i])
+            c1.record()
+            torch.cuda.synchronize()
+            c2ms = c0.elapsed_time(c1) / reps
+            cms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+            rms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+            bc, br = P2 * 4 + 1 + K2 * 8, P2 * 4 + K2 * 4 + 4
+            line['configs1_leg'] = dict(
+                workload='configs[1]: 2D worms 696x520, patchshape 1x41x41, dense f32 input',
+                fg_voxels=n2, ms_per_image=c2ms, value=n2 / (c2ms * 1e-3) / 1e6, unit='Mvoxels/s',
+                consensus=dict(kernel_ms=cms, bytes_per_fg_voxel=bc,
+                               achieved=bc * n2 / (cms * 1e-3) / 1e9,
+                               frac=bc * n2 / (cms * 1e-3) / 1e9 / peak),
+                rank=dict(kernel_ms=rms, bytes_per_fg_voxel=br,
+                          achieved=br * n2 / (rms * 1e-3) / 1e9,
+                          frac=br * n2 / (rms * 1e-3) / 1e9 / peak))
+            del pred2
+        except Exception as e:
+            line['configs1_leg'] = dict(failed=repr(e))
     if not args.no_cpu_baseline and world == 1:
         try:
             cores = all_host_threads()

@@ -567,7 +567,7 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
             pairs = got[0].astype(np.int64) + np.tile(start, 2)      # :650 and :162
             return pairs.astype(np.uint32), got[1]
         pipeline.run_blocks(my_blocks, steps, max_inflight=int(kwargs.get('ppp_inflight', 16)),
-                            on_done=block_done)
+                            n_streams=int(kwargs.get('ppp_streams', 8)), on_done=block_done)
     else:
         res = _run_jobs(my_blocks,
                         lambda b: _block_job(shard, offsets[b], chunksize, ps, kwargs, block_fn),
