@@ -42,12 +42,18 @@ from .stitch_patch_graph import (get_offsets, face_candidates, face_pairs, _dist
 logger = logging.getLogger(__name__)
 
 
-def slab_partition(shape, chunksize, world, axis=None, weights=None):
+def slab_partition(shape, chunksize, world, axis=None, weights=None, bb_offset=None,
+                   bb_shape=None):
     """block rows along `axis` dealt to the ranks in contiguous runs.
     weights: cost of every block row along `axis` (e.g. its foreground count); the
     runs then minimise the largest per-rank cost, else they hold equal row counts.
+    bb_offset / bb_shape: the block grid covers this box only (`only_bb`,
+    stitch_patch_graph.py:745-771); the first / last non-empty slab is extended to the
+    volume border (the halos of the outer blocks reach beyond the box).
     Returns (axis, [(lo, hi)] * world) in voxels; empty slabs have lo == hi."""
-    shape = [int(s) for s in shape]
+    full = [int(s) for s in shape]
+    org = [0, 0, 0] if bb_offset is None else [int(v) for v in bb_offset]
+    shape = full if bb_shape is None else [int(s) for s in bb_shape]
     chunk = [int(min(c, s)) for c, s in zip(chunksize, shape)]
     nrows = [-(-s // c) for s, c in zip(shape, chunk)]
     if axis is None:
@@ -76,7 +82,12 @@ def slab_partition(shape, chunksize, world, axis=None, weights=None):
     out = []
     for r in range(world):
         a, b = cuts[r], cuts[r + 1]
-        out.append((min(a * chunk[axis], shape[axis]), min(b * chunk[axis], shape[axis])))
+        out.append((org[axis] + min(a * chunk[axis], shape[axis]),
+                    org[axis] + min(b * chunk[axis], shape[axis])))
+    live = [r for r in range(world) if out[r][1] > out[r][0]]
+    if live:
+        out[live[0]] = (0, out[live[0]][1])
+        out[live[-1]] = (out[live[-1]][0], full[axis])
     return axis, out
 
 
@@ -90,7 +101,7 @@ class RowShard:
     numinst  u8 [G] instance-count class of the voxel (overlap = numinst > 1), or None
     """
 
-    def __init__(self, shape, axis, lo, hi, coords, patches, numinst=None):
+    def __init__(self, shape, axis, lo, hi, coords, patches, numinst=None, fg=None):
         import torch
         self.shape = tuple(int(s) for s in shape)
         self.axis, self.lo, self.hi = int(axis), int(lo), int(hi)
@@ -98,6 +109,9 @@ class RowShard:
         self.patches = patches.contiguous()
         assert patches.dtype == torch.float16
         self.numinst = None if numinst is None else numinst.to(torch.uint8).contiguous()
+        # host-side foreground of the stored voxels (fg_key / numinst rule,
+        # utilVoteInstances.py:306-322); None: the centre channel decides
+        self.fg = None if fg is None else fg.to(torch.uint8).contiguous()
         self.dev = patches.device
         self.ext_lo, self.ext_hi = self.lo, self.hi
         self.vox2row = None
@@ -115,7 +129,8 @@ class RowShard:
         S = self.shape[self.axis]
         ext = [(max(lo - halo, 0), min(hi + halo, S)) if hi > lo else (lo, hi) for lo, hi in slabs]
         self.ext_lo, self.ext_hi = ext[rank]
-        coords, patches, numinst = self.coords, self.patches, self.numinst
+        coords, patches = self.coords, self.patches
+        extras = [self.numinst, self.fg]            # optional u8 [G] columns, same on all ranks
         if world > 1:
             a = coords[:, self.axis]
             send_idx = []
@@ -144,8 +159,7 @@ class RowShard:
                 if ns:
                     idx = send_idx[d]
                     bufs = [coords[idx].contiguous(), patches[idx].contiguous()]
-                    if numinst is not None:
-                        bufs.append(numinst[idx].contiguous())
+                    bufs += [e[idx].contiguous() for e in extras if e is not None]
                     keep.append(bufs)
                     for b in bufs:
                         ops.append(dist.P2POp(dist.isend, b.to(cdev), d))
@@ -153,8 +167,8 @@ class RowShard:
                 if nr:
                     bufs = [torch.empty((nr, 3), dtype=torch.int32, device=cdev),
                             torch.empty((nr, P), dtype=torch.float16, device=cdev)]
-                    if numinst is not None:
-                        bufs.append(torch.empty(nr, dtype=torch.uint8, device=cdev))
+                    bufs += [torch.empty(nr, dtype=torch.uint8, device=cdev)
+                             for e in extras if e is not None]
                     recv.append(bufs)
                     for b in bufs:
                         ops.append(dist.P2POp(dist.irecv, b, d))
@@ -164,9 +178,13 @@ class RowShard:
             if recv:
                 coords = torch.cat([coords] + [b[0].to(self.dev) for b in recv])
                 patches = torch.cat([patches] + [b[1].to(self.dev) for b in recv])
-                if numinst is not None:
-                    numinst = torch.cat([numinst] + [b[2].to(self.dev) for b in recv])
-        self.coords, self.patches, self.numinst = coords, patches, numinst
+                k = 2
+                for i, e in enumerate(extras):
+                    if e is not None:
+                        extras[i] = torch.cat([e] + [b[k].to(self.dev) for b in recv])
+                        k += 1
+        self.coords, self.patches = coords, patches
+        self.numinst, self.fg = extras
         self._index()
 
     def _index(self):
@@ -208,7 +226,7 @@ class RowShard:
         valid = v2r >= 0
         idx = v2r.clamp(min=0).long()
         th = float(np.float32(getFgThreshold(**kwargs)))
-        fg = valid & (self.mid[idx] > th)
+        fg = valid & ((self.mid[idx] > th) if self.fg is None else (self.fg[idx] != 0))
         if self.numinst is not None:
             numinst = torch.where(valid, self.numinst[idx], torch.zeros((), dtype=torch.uint8,
                                                                        device=self.dev))
@@ -462,11 +480,14 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
     ps = np.asarray(kwargs['patchshape'])
     shape = shard.shape
     axis = shard.axis
-    chunksize = np.minimum(np.asarray(kwargs['chunksize']), shape)
+    # only_bb (stitch_patch_graph.py:745-771, 137-138): block grid over the bounding box
+    bb_offset = np.asarray(kwargs.pop('bb_offset', np.zeros(3, int)), dtype=int)
+    bb_shape = np.asarray(kwargs.pop('bb_shape', shape), dtype=int)
+    chunksize = np.minimum(np.asarray(kwargs['chunksize']), bb_shape)
     kwargs = dict(kwargs, chunksize=chunksize)
     if workers is None:
         workers = int(kwargs.get('ppp_block_workers', 6))
-    offsets = get_offsets(shape, chunksize)
+    offsets = [o + bb_offset for o in get_offsets(bb_shape, chunksize)]
     nblk = len(offsets)
 
     def slab_of(coord):
@@ -723,3 +744,40 @@ def gather_slabs(inst, slabs, axis, shape, dst=0):
         for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, inst.to(cdev).contiguous(), dst)]):
             w.wait()
     return None
+
+
+def rows_from_dense(pred, foreground, numinst, axis, lo, hi, device, th, tile=32):
+    """the compact rows of the slab lo <= coord[axis] < hi of a DENSE prediction
+    (numpy / zarr-like [P,Z,Y,X]): every voxel whose centre channel passes `th` or that
+    the host-side `foreground` (bool [Z,Y,X]) names -- the only voxels whose patches the
+    assembly ever reads.  Read `tile` planes at a time, so the dense volume is never held.
+    Returns (coords i32 [G,3], patches f16 [G,P], numinst u8 [G], fg u8 [G]) on `device`."""
+    import torch
+    P = int(pred.shape[0])
+    mid = P // 2
+    cs, ps_, ns, fs = [], [], [], []
+    for a in range(lo, hi, tile):
+        b = min(a + tile, hi)
+        sl = [slice(None)] * 3
+        sl[axis] = slice(a, b)
+        blk = np.asarray(pred[(slice(None),) + tuple(sl)])
+        fgs = np.asarray(foreground[tuple(sl)]) != 0
+        keep = (blk[mid].astype(np.float32) > np.float32(th)) | fgs
+        c = np.argwhere(keep)
+        if len(c) == 0:
+            continue
+        ps_.append(np.ascontiguousarray(blk[:, c[:, 0], c[:, 1], c[:, 2]].T.astype(np.float16)))
+        fs.append(fgs[c[:, 0], c[:, 1], c[:, 2]].astype(np.uint8))
+        ns.append(np.asarray(numinst[tuple(sl)])[c[:, 0], c[:, 1], c[:, 2]].astype(np.uint8))
+        c[:, axis] += a
+        cs.append(c.astype(np.int32))
+    if not cs:
+        return (torch.zeros((0, 3), dtype=torch.int32, device=device),
+                torch.zeros((0, P), dtype=torch.float16, device=device),
+                torch.zeros(0, dtype=torch.uint8, device=device),
+                torch.zeros(0, dtype=torch.uint8, device=device))
+    # raster order over the slab (tiles are raster-ordered only along `axis` == 0)
+    c = np.concatenate(cs)
+    order = np.lexsort((c[:, 2], c[:, 1], c[:, 0]))
+    cat = lambda parts: torch.from_numpy(np.concatenate(parts)[order]).to(device)
+    return cat(cs), cat(ps_), cat(ns), cat(fs)

@@ -471,6 +471,37 @@ def gather_patches(pred, z, y, x, tile=64):
     return out
 
 
+def _main_rows(inputs, bb, **kwargs):
+    """the volume as compact rows, one slab per rank, through sharded.stitch_shard.
+    Returns (instances u32 [Z,Y,X] on rank 0 (zeros elsewhere), foreground bool)."""
+    import torch
+    from . import sharded
+    from .utilVoteInstances import getFgThreshold
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    dev = torch.device('cuda', torch.cuda.current_device())
+    shape = inputs.shape
+    foreground, numinst = inputs._fg_numinst(np.zeros(3, int), np.asarray(shape), **kwargs)
+    axis, _ = sharded.slab_partition(shape, kwargs['chunksize'], world, bb_offset=bb[0],
+                                     bb_shape=bb[1])
+    csz = int(min(kwargs['chunksize'][axis], bb[1][axis]))
+    per_plane = foreground.sum(axis=tuple(a for a in range(3) if a != axis))
+    o = int(bb[0][axis])
+    weights = [int(per_plane[o + i:o + i + csz].sum()) for i in range(0, int(bb[1][axis]), csz)]
+    axis, slabs = sharded.slab_partition(shape, kwargs['chunksize'], world, axis=axis,
+                                         weights=weights, bb_offset=bb[0], bb_shape=bb[1])
+    lo, hi = slabs[rank]
+    th = float(np.float32(getFgThreshold(**kwargs)))
+    c, p, ni, fgr = sharded.rows_from_dense(inputs.pred, foreground, numinst, axis, lo, hi, dev, th)
+    shard = sharded.RowShard(shape, axis, lo, hi, c, p, ni, fgr)
+    inst, _ = sharded.stitch_shard(shard, slabs, bb_offset=bb[0], bb_shape=bb[1], **kwargs)
+    full = sharded.gather_slabs(inst, slabs, axis, shape)
+    if full is None:
+        return np.zeros(shape, np.uint32), foreground
+    return full.cpu().numpy().astype(np.uint32), foreground
+
+
 def main(pred_file, result_folder='.', **kwargs):
     """stitch_patch_graph.py:672-896: file-level entry point (zarr in,
     `<sample>.hdf` / `.npz` out).  Under torch.distributed every rank works, rank 0
@@ -496,12 +527,17 @@ def main(pred_file, result_folder='.', **kwargs):
         logger.info('Volume has no foreground voxel, returning...')
         return
     dist = _dist()
-    cache = None
-    if kwargs.get('ppp_block_cache', True) and (dist is None or dist.get_world_size() == 1):
-        from .io_util import open_zarr
-        cache = open_zarr(os.path.join(result_folder, sample + '.zarr'), 'a')
-    instances, foreground, _ = stitch_arrays(inputs, bb_offset=bb[0], bb_shape=bb[1],
-                                             block_cache=cache, **kwargs)
+    if kwargs.get('ppp_rows', dist is not None):
+        # compact rows, the volume sharded over the ranks (sharded.py): the default under
+        # torch.distributed, `ppp_rows=True` selects it for a single process as well
+        instances, foreground = _main_rows(inputs, bb, **kwargs)
+    else:
+        cache = None
+        if kwargs.get('ppp_block_cache', True):
+            from .io_util import open_zarr
+            cache = open_zarr(os.path.join(result_folder, sample + '.zarr'), 'a')
+        instances, foreground, _ = stitch_arrays(inputs, bb_offset=bb[0], bb_shape=bb[1],
+                                                 block_cache=cache, **kwargs)
     if dist is None or dist.get_rank() == 0:
         os.makedirs(result_folder, exist_ok=True)
         out = finish_outputs(instances, foreground, **kwargs)

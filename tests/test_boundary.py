@@ -257,6 +257,9 @@ def test_blockwise_entry_point_with_flylight_toml(tmp_path):
                                   paint_fn=host_logic.oracle_paint_fn, bb_offset=bb[0],
                                   bb_shape=bb[1], **dict(kw))
     assert np.array_equal(inst.astype(np.uint16), ref.astype(np.uint16))
+    # the same call on the compact-row engine (sharded.py; the default under torchrun)
+    rows = spg.main(path, result_folder=str(tmp_path / 'out_rows'), **dict(kw, ppp_rows=True))
+    assert np.array_equal(rows.astype(np.uint16), inst.astype(np.uint16))
     # second call: every block and face comes from the cache (skip-if-exists, :584-587)
     cache = io_util.open_zarr(os.path.join(out_dir, 'sample.zarr'))
     assert len(cache['volumes/blocks'].keys()) > 1

@@ -103,6 +103,42 @@ def test_slab_partition():
     assert slabs == [(0, 64), (64, 100)]
 
 
+def test_slab_partition_with_bounding_box_and_weights():
+    # block grid over the box [10, 10+80) along y, chunks of 20: rows start at 10, 30, 50, 70
+    axis, slabs = sharded.slab_partition((16, 120, 40), (16, 20, 40), 2, bb_offset=(0, 10, 0),
+                                         bb_shape=(16, 80, 40))
+    assert axis == 1 and slabs == [(0, 50), (50, 120)]
+    # heavy first row: it gets a rank of its own
+    axis, slabs = sharded.slab_partition((16, 120, 40), (16, 20, 40), 2, bb_offset=(0, 10, 0),
+                                         bb_shape=(16, 80, 40), weights=[10, 1, 1, 1])
+    assert slabs == [(0, 30), (30, 120)]
+    # more ranks than rows: the spare ones stay empty, the outer ones reach the borders
+    axis, slabs = sharded.slab_partition((16, 120, 40), (16, 40, 40), 4, bb_offset=(0, 10, 0),
+                                         bb_shape=(16, 80, 40))
+    live = [s for s in slabs if s[1] > s[0]]
+    assert len(live) == 2 and live[0][0] == 0 and live[-1][1] == 120
+
+
+def test_rows_from_dense_keeps_what_the_assembly_reads():
+    import torch
+    rng = np.random.default_rng(2)
+    pred = rng.random((27, 6, 10, 12)).astype(np.float16)
+    fg = rng.random((6, 10, 12)) < 0.2
+    ni = rng.integers(0, 3, (6, 10, 12)).astype(np.uint8)
+    for axis, lo, hi in ((0, 0, 6), (1, 3, 9), (2, 4, 12)):
+        c, p, n, f = sharded.rows_from_dense(pred, fg, ni, axis, lo, hi, 'cpu', 0.5, tile=4)
+        keep = (pred[13].astype(np.float32) > 0.5) | fg
+        sl = [slice(None)] * 3
+        sl[axis] = slice(lo, hi)
+        want = np.argwhere(keep[tuple(sl)])
+        want[:, axis] += lo
+        cc = c.numpy()
+        assert np.array_equal(cc, want)
+        assert np.array_equal(p.numpy(), pred[:, cc[:, 0], cc[:, 1], cc[:, 2]].T)
+        assert np.array_equal(n.numpy(), ni[cc[:, 0], cc[:, 1], cc[:, 2]])
+        assert np.array_equal(f.numpy() != 0, fg[cc[:, 0], cc[:, 1], cc[:, 2]])
+
+
 def test_sharded_world1_oracle_engine_matches_reference_golden():
     g, kw, pred, numinst = _load()
     inst, info, _, _ = _run_rank(pred, numinst, kw, 0, 1)
