@@ -355,3 +355,60 @@ def test_pair_order_fallback_without_the_set_replay(monkeypatch):
     slow = assembly.query_pairs_filtered(tree, pts, 42, thr)
     slow2 = assembly.query_pairs_set_order(tree, 42)
     assert len(fast) > 100 and np.array_equal(fast, slow) and np.array_equal(fast2, slow2)
+
+
+# ---------------------------------------------------------------------------
+# the pre-crop and the post side against a run of the reference's own blockwise driver
+# (tools/gen_golden.py blockwise_bb: only_bb + ignore_small_comps, remove_small_comps +
+# relabel with the reference's util functions, dilated and masked outputs, mws)
+# ---------------------------------------------------------------------------
+def _bb_golden():
+    from tests.golden_util import bb_case
+    g = dict(np.load(os.path.join(HERE, 'golden', 'blockwise3d_bb_post.npz')))
+    kw = json.loads(str(g['kwargs']))
+    ps, skw, pred, numinst = bb_case()
+    prob = np.stack([(numinst == 0), (numinst == 1), (numinst > 1)]).astype(np.float32)
+    return g, kw, pred, numinst, prob
+
+
+_BB_KEYS = ('vote_instances', 'vote_foreground', 'vote_instances_masked', 'vote_instances_dil_1',
+            'vote_instances_masked_dil_1')
+
+
+def test_bounding_box_grid_and_post_side_match_the_reference_run():
+    """host logic (bbox, block grid at the box corner, post-processing) with the oracle as
+    block engine: the five output volumes of the reference's run, value for value."""
+    from oracle import host_logic
+    g, kw, pred, numinst, prob = _bb_golden()
+    inputs = spg.VolumeInputs(pred.astype(np.float16), numinst_prob=prob)
+    bb = spg.bounding_box(inputs, **kw)
+    # the block keys the reference wrote start at the box corner
+    blocks = {str(k).split('/')[2] for k in g['block_keys'] if str(k).count('/') == 3}
+    offs = {spg.get_offset_str(o + bb[0]) for o in spg.get_offsets(bb[1], np.minimum(
+        kw['chunksize'], bb[1]))}
+    assert spg.get_offset_str(bb[0]) in blocks and blocks <= offs
+    inst, fg, _ = spg.stitch_arrays(inputs, block_fn=host_logic.oracle_block_fn,
+                                    paint_fn=host_logic.oracle_paint_fn, bb_offset=bb[0],
+                                    bb_shape=bb[1], **kw)
+    out = spg.finish_outputs(inst, fg, **kw)
+    for k in _BB_KEYS:
+        assert np.array_equal(out[k], g[k].astype(np.uint16)), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('rows', [False, True])
+def test_file_level_entry_matches_the_reference_run(tmp_path, rows):
+    """stitch_patch_graph.main on a zarr store, dense engine and compact-row engine."""
+    g, kw, pred, numinst, prob = _bb_golden()
+    path = str(tmp_path / 'sample.zarr')
+    z = io_util.ZarrLiteGroup(path, 'w')
+    z.create_dataset('volumes/pred_affs', data=pred.astype(np.float16), chunks=(125, 10, 30, 30))
+    z.create_dataset('volumes/pred_numinst', data=prob, chunks=(3, 10, 30, 30))
+    out_dir = str(tmp_path / 'out')
+    spg.main(path, result_folder=out_dir, **dict(kw, ppp_rows=rows))
+    fn = os.path.join(out_dir, 'sample.npz')
+    if not os.path.exists(fn):
+        pytest.skip("h5py present: .hdf written, checked elsewhere")
+    res = np.load(fn)
+    for k in _BB_KEYS:
+        assert np.array_equal(res[k], g[k].astype(np.uint16)), k

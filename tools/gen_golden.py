@@ -401,6 +401,61 @@ def run_blockwise_big(S):
     print('blockwise3d_3x3x3_mws %.2f MB' % (os.path.getsize(fn) / 1e6))
 
 
+from tests.golden_util import bb_case  # noqa: E402
+
+
+def run_blockwise_bb(S):
+    """the reference's blockwise driver with the flylight pre-crop and post side:
+    only_bb + ignore_small_comps (clean_mask), remove_small_comps + relabel, dilated and
+    masked outputs (stitch_patch_graph.py:745-764, 824-894), mws partition."""
+    import hashlib
+    import importlib.util
+    import shutil
+    sp = ref_runner.load_stitch_module(S)
+    spec = importlib.util.spec_from_file_location(
+        'ppp_ref_postprocess', os.path.join(ref_runner.REF_ROOT, 'PatchPerPix', 'util',
+                                            'postprocess.py'))
+    post = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(post)
+    sp.remove_small_components = post.remove_small_components     # the real ones
+    sp.relabel = post.relabel
+    sp.io.imsave = lambda *a, **k: None
+    ps, skw, pred, numinst = bb_case()
+    root = '/tmp/ppp_gold_bb'
+    shutil.rmtree(root, ignore_errors=True)
+    pred_path = os.path.join(root, 'sample.zarr')
+    store = ref_runner.FakeGroup.open(pred_path, 'w')
+    store['volumes/pred_affs'] = pred.astype(np.float16)
+    prob = np.stack([(numinst == 0), (numinst == 1), (numinst > 1)]).astype(np.float32)
+    store['volumes/pred_numinst'] = prob
+    kw = S.default_kwargs(
+        blockwise=True, chunksize=[12, 22, 22], patchshape=[5, 5, 5],
+        aff_key='volumes/pred_affs', numinst_key='volumes/pred_numinst', fg_key=None,
+        numinst_threshs=[0.9, 0.1], only_bb=True, output_format='hdf',
+        num_parallel_blocks=1, ignore_small_comps=30, skeletonize_foreground=False,
+        remove_small_comps=60, dilate_instances=True, res_key='vote_instances', mws=True)
+    del kw['result_folder']
+    t0 = time.time()
+    sp.main(pred_path, result_folder=os.path.join(root, 'out'), **kw)
+    out = ref_runner.FakeGroup.open(os.path.join(root, 'out', 'sample.hdf'))
+    res = {k: np.asarray(out[k]) for k in ('vote_instances', 'vote_foreground',
+                                           'vote_instances_masked', 'vote_instances_dil_1',
+                                           'vote_instances_masked_dil_1')}
+    blk = ref_runner.FakeGroup.open(os.path.join(root, 'out', 'sample.zarr'))
+    res['block_keys'] = np.array(sorted(k for k in blk.d if k.endswith('patch_pairs')))
+    res.update(
+        pred_sha1=hashlib.sha1(pred.astype(np.float16).tobytes()).hexdigest(),
+        patchshape=ps.astype(np.int32),
+        kwargs=json.dumps({k: v for k, v in kw.items()
+                           if isinstance(v, (bool, int, float, str, list)) or v is None}))
+    fn = os.path.join(GOLD, 'blockwise3d_bb_post.npz')
+    np.savez_compressed(fn, **res)
+    print('blockwise3d_bb_post %.1fs inst=%d blocks+faces=%d  %.2f MB' % (
+        time.time() - t0, len(np.unique(res['vote_instances'])) - 1, len(res['block_keys']),
+        os.path.getsize(fn) / 1e6))
+    print(res['block_keys'][:6])
+
+
 def run_mws(S):
     """mutex-watershed labelling (kwargs mws=True, the flylight default): the
     reference's setAffgraph + affGraphToInstances on the recorded pairs / aff of
@@ -512,6 +567,9 @@ def main():
         return 0
     if sys.argv[1:] == ['mws']:
         run_mws(ref_runner.RefSession())
+        return 0
+    if sys.argv[1:] == ['blockwise_bb']:
+        run_blockwise_bb(ref_runner.RefSession())
         return 0
     if sys.argv[1:] == ['blockwise3']:
         run_blockwise_big(ref_runner.RefSession())
