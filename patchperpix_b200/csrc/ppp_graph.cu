@@ -176,7 +176,13 @@ patch_graph_kernel(Src pred, const uint8_t* __restrict__ flags,
 // thread 0 adds the previous chunk in order.  The chain of ~n1*n2 dependent
 // FADDs of a pair bounds its latency; many light CTAs per SM run side by side.
 // ---------------------------------------------------------------------------
-#define PGR_THREADS 96          // warp 0 adds, warps 1-2 produce
+#ifndef PGR_THREADS
+#define PGR_THREADS 160         // warp 0 adds, the other four warps produce (0.77 vs 0.81 ms with two)
+#endif
+#define PGR_STR2(x) #x
+#define PGR_STR(x) PGR_STR2(x)
+#define PGR_NT PGR_STR(PGR_THREADS)
+#define PGR_PROD (PGR_THREADS - 32)
 #define PGR_CH 256
 #define PGR_BIAS 512
 
@@ -261,7 +267,7 @@ patch_graph_ref_kernel(Src pred, const uint8_t* __restrict__ flags,
     uint32_t* s_pw2 = s_pw1 + g.P;                //     (only with LCG)
     __shared__ int s_scr1[18], s_scr2[18];
     __shared__ __align__(16) float s_val[2][PGR_CH];
-    __shared__ unsigned s_cnt[2];
+    __shared__ unsigned s_cnt[PGR_PROD / 32];
 
     const int64_t id = blockIdx.x;
     const int tid = threadIdx.x;
@@ -310,19 +316,19 @@ patch_graph_ref_kernel(Src pred, const uint8_t* __restrict__ flags,
     if (tid >= 32) {
         // ---- producer warps: chunk c of the flattened (i, j) sequence -> s_val[c & 1] ----
         const int pt = tid - 32;                  // 0..63
-        constexpr int TPT = PGR_CH / 64;          // terms per producer thread and chunk
+        constexpr int TPT = PGR_CH / PGR_PROD;    // terms per producer thread and chunk
         unsigned cnt = 0;
         int ic = 0, jc = 0;                       // (i, j) of the first term of the chunk
         for (int c = 0; c < nch; c++) {
             if (c >= 2) {                                         // buffer c&1 was consumed
-                if (c & 1) asm volatile("bar.sync 5, 96;\n" ::: "memory");
-                else asm volatile("bar.sync 4, 96;\n" ::: "memory");
+                if (c & 1) asm volatile("bar.sync 5, " PGR_NT ";\n" ::: "memory");
+                else asm volatile("bar.sync 4, " PGR_NT ";\n" ::: "memory");
             }
             float* dst = s_val[c & 1];
             int64_t addr[TPT];
 #pragma unroll
             for (int u = 0; u < TPT; u++) {
-                int i = ic, j = jc + pt + 64 * u;
+                int i = ic, j = jc + pt + PGR_PROD * u;
                 while (j >= n2 && i < n1) { j -= n2; i++; }
                 addr[u] = -1;
                 if (i < n1) {
@@ -354,12 +360,12 @@ patch_graph_ref_kernel(Src pred, const uint8_t* __restrict__ flags,
             }
 #pragma unroll
             for (int u = 0; u < TPT; u++)
-                dst[pt + 64 * u] = addr[u] >= 0 ? cons[addr[u]] : 0.0f;
+                dst[pt + PGR_PROD * u] = addr[u] >= 0 ? cons[addr[u]] : 0.0f;
             jc += PGR_CH;
             while (jc >= n2 && ic < n1) { jc -= n2; ic++; }
             __threadfence_block();
-            if (c & 1) asm volatile("bar.arrive 3, 96;\n" ::: "memory");     // chunk c is ready
-            else asm volatile("bar.arrive 2, 96;\n" ::: "memory");
+            if (c & 1) asm volatile("bar.arrive 3, " PGR_NT ";\n" ::: "memory");     // chunk c is ready
+            else asm volatile("bar.arrive 2, " PGR_NT ";\n" ::: "memory");
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) s_cnt[(tid >> 5) - 1] = cnt;
@@ -367,8 +373,8 @@ patch_graph_ref_kernel(Src pred, const uint8_t* __restrict__ flags,
         // ---- adder warp: lane 0 adds the chunks in order ---------------------------------
         float acc = 0.0f;
         for (int c = 0; c < nch; c++) {
-            if (c & 1) asm volatile("bar.sync 3, 96;\n" ::: "memory");       // wait for chunk c
-            else asm volatile("bar.sync 2, 96;\n" ::: "memory");
+            if (c & 1) asm volatile("bar.sync 3, " PGR_NT ";\n" ::: "memory");       // wait for chunk c
+            else asm volatile("bar.sync 2, " PGR_NT ";\n" ::: "memory");
             if (lane == 0) {
                 const float4* v = (const float4*)s_val[c & 1];
 #pragma unroll 8
@@ -379,8 +385,8 @@ patch_graph_ref_kernel(Src pred, const uint8_t* __restrict__ flags,
             }
             if (c + 2 < nch) {                                    // buffer free
                 __syncwarp();
-                if (c & 1) asm volatile("bar.arrive 5, 96;\n" ::: "memory");
-                else asm volatile("bar.arrive 4, 96;\n" ::: "memory");
+                if (c & 1) asm volatile("bar.arrive 5, " PGR_NT ";\n" ::: "memory");
+                else asm volatile("bar.arrive 4, " PGR_NT ";\n" ::: "memory");
             }
         }
         __syncwarp();
@@ -388,7 +394,8 @@ patch_graph_ref_kernel(Src pred, const uint8_t* __restrict__ flags,
     }
     __syncthreads();
     if (tid == 0) {
-        const unsigned c = s_cnt[0] + s_cnt[1];
+        unsigned c = 0;
+        for (int q = 0; q < PGR_PROD / 32; q++) c += s_cnt[q];
         const float acc = s_val[0][0];
         aff[id] = (cfg.graph_flags & 1) ? acc / (float)(c > 1 ? c : 1) : acc;
     }

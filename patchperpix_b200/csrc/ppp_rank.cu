@@ -467,8 +467,8 @@ extern "C" int ppp_rank(const float* dp, const uint8_t* flags, const int32_t* fg
     case 1: RR_LAUNCH(4, 4, 2); break;
     case 2: RR_LAUNCH(8, 4, 1); break;
     case 3: RR_LAUNCH(4, 4, 1); break;
-    case 4: RR_LAUNCH(2, 2, 8); break;
-    case 5: RR_LAUNCH(2, 2, 4); break;
+    case 4: RR_LAUNCH(4, 2, 2); break;
+    case 5: RR_LAUNCH(2, 2, 2); break;
     case 6: RR_LAUNCH(8, 4, 2); break;
     case 7: RR_LAUNCH(4, 2, 4); break;
     default: RR_LAUNCH(4, 4, 4); break;
