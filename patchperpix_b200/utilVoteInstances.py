@@ -24,15 +24,19 @@ def getFgThreshold(**kwargs):
 
 
 def numinst_from_prob(numinst_prob, **kwargs):
-    """utilVoteInstances.py:263-271."""
-    numinst_prob = np.squeeze(numinst_prob)
-    if len(numinst_prob.shape) == 3:
-        numinst_prob = np.expand_dims(numinst_prob, axis=1)
-    numinst = np.argmax(numinst_prob, axis=0).astype(np.uint8)
-    if kwargs.get('numinst_threshs'):
-        numinst = np.zeros(numinst_prob.shape[1:], dtype=np.uint8)
-        for i in range(len(kwargs['numinst_threshs'])):
-            numinst[numinst_prob[i + 1] > kwargs['numinst_threshs'][i]] = i + 1
+    """instance-count class per voxel from the class probabilities [C,(Z,)Y,X]
+    (utilVoteInstances.py:263-271): with `numinst_threshs` = (t1, t2, ...) class i is taken
+    where prob[i] > t_i, later classes overriding earlier ones, else 0; without them the
+    arg-max class."""
+    prob = np.squeeze(np.asarray(numinst_prob))
+    if prob.ndim == 3:                      # 2-D data: [C,Y,X] -> [C,1,Y,X]
+        prob = prob[:, None]
+    threshs = kwargs.get('numinst_threshs')
+    if not threshs:
+        return np.argmax(prob, axis=0).astype(np.uint8)
+    numinst = np.zeros(prob.shape[1:], dtype=np.uint8)
+    for cls, th in enumerate(threshs, start=1):
+        numinst[prob[cls] > th] = cls
     return numinst
 
 
@@ -80,14 +84,17 @@ def returnFg(affs, numinst, fg, **kwargs):
 
 
 def getResKey(**kwargs):
-    res_ext = '_' + str(kwargs['patch_threshold']).replace('.', '')
+    """suffix of the result datasets when `add_suffix` is set (utilVoteInstances.py:325-337):
+    _<threshold digits>[_tfgc][_mws][_smp<sample digits>]."""
+    digits = lambda v: str(v).replace('.', '')
+    parts = [digits(kwargs['patch_threshold'])]
     if not kwargs.get('skipThinCover', False):
-        res_ext += "_tfgc"
+        parts.append('tfgc')                # thinned foreground cover
     if kwargs['mws']:
-        res_ext += "_mws"
+        parts.append('mws')
     if kwargs['sample'] < 1.0:
-        res_ext += "_smp" + str(kwargs['sample']).replace('.', '')
-    return res_ext
+        parts.append('smp' + digits(kwargs['sample']))
+    return '_' + '_'.join(parts)
 
 
 def _open(aff_file):

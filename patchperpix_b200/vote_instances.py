@@ -29,14 +29,14 @@ _UNSUPPORTED = ('isbiHack', 'debug', 'graphToInst', 'use_score_oracle',
 
 
 def merge_dicts(sink, source):
-    """vote_instances.py:49-59."""
-    if not isinstance(sink, dict) or not isinstance(source, dict):
+    """overlay `source` on `sink` in place, descending into sub-dicts present on both
+    sides (the call-site helper of vote_instances.py:49-59, kept for callers that import
+    it)."""
+    if not (isinstance(sink, dict) and isinstance(source, dict)):
         raise TypeError('Args to merge_dicts should be dicts')
-    for k, v in source.items():
-        if isinstance(source[k], dict) and isinstance(sink.get(k), dict):
-            sink[k] = merge_dicts(sink[k], v)
-        else:
-            sink[k] = v
+    for key, val in source.items():
+        both = isinstance(val, dict) and isinstance(sink.get(key), dict)
+        sink[key] = merge_dicts(sink[key], val) if both else val
     return sink
 
 
@@ -382,45 +382,49 @@ def do_all(aff_file, patchshape=np.array([1, 25, 25]), **kwargs):
                  kwargs.get('output_format', 'hdf'))
 
 
+# what the reference's argument parser would fill in for keys a caller leaves out
+# (vote_instances.py:62-147)
+_MAIN_DEFAULTS = dict(
+    affinities=None, affinities_key="images/pred_affs", basedir=None, mode=None,
+    checkpoint=None, debug=False, patch_threshold=0.9, fc_threshold=0.5, consensus=None,
+    scores=None, ranked_patches=None, aff_graph=None, selected_patches=None,
+    selected_patch_pairs=None, select_patches_for_sparse_data=False, cuda=False,
+    skipLookup=False, skipThinCover=False, skipRanking=False, skipConsensus=False,
+    termAfterThinCover=False, graphToInst=False, mws=False, includeSinglePatchCCS=False,
+    removeIntersection=False, isbiHack=False, mask_fg_border=False, parallel=False,
+    save_no_intermediates=False)
+
+
+def _input_files(args):
+    """the prediction files one call of main() covers (vote_instances.py:581-600): a zarr
+    store or a single file, every .hdf / .npy of a directory, or the processed files of
+    <basedir>/<mode>/processed/<checkpoint>."""
+    src = args['affinities']
+    if src is None:
+        if args['mode'] is None or args['checkpoint'] is None:
+            return []
+        return glob.glob(os.path.join(args['basedir'], args['mode'], "processed",
+                                      args['checkpoint'], "*.hdf"))
+    if src.endswith(".zarr") or os.path.isfile(src):
+        return [src]
+    if os.path.isdir(src):
+        return [f for ext in ("*.hdf", "*.npy") for f in glob.glob(os.path.join(src, ext))]
+    raise RuntimeError("affinities (%s) should be file or dir" % src)
+
+
 def main(**kwargs):
-    """vote_instances.py:557-605 (without re-parsing sys.argv)."""
-    args = dict(affinities=None, affinities_key="images/pred_affs", basedir=None,
-                mode=None, checkpoint=None, debug=False, patch_threshold=0.9,
-                fc_threshold=0.5, consensus=None, scores=None, ranked_patches=None,
-                aff_graph=None, selected_patches=None, selected_patch_pairs=None,
-                select_patches_for_sparse_data=False, cuda=False, skipLookup=False,
-                skipThinCover=False, skipRanking=False, skipConsensus=False,
-                termAfterThinCover=False, graphToInst=False, mws=False,
-                includeSinglePatchCCS=False, removeIntersection=False,
-                isbiHack=False, mask_fg_border=False, parallel=False,
-                save_no_intermediates=False)       # argparse defaults, :62-147
-    if len(kwargs) > 0:
-        args = merge_dicts(args, kwargs)
+    """vote_instances.py:557-605: keyword arguments over the parser's defaults (sys.argv is
+    not re-parsed), one do_all per input file."""
+    args = merge_dicts(dict(_MAIN_DEFAULTS), kwargs)
     if 'check_required' in kwargs:
-        assert type(args.get('patchshape')) in [np.ndarray, tuple, list], \
-            "Please check type of patchshape {}".format(type(args.get('patchshape')))
-        assert type(args.get('result_folder')) == str, \
-            "Please check type of result_folder {}".format(type(args.get('result_folder')))
+        for key, kinds in (('patchshape', (np.ndarray, tuple, list)), ('result_folder', (str,))):
+            assert type(args.get(key)) in kinds, \
+                "Please check type of {} {}".format(key, type(args.get(key)))
+    if args['parallel']:
+        raise NotImplementedError("parallel=True (a process pool over files) is not built")
     if args.get('cuda') and not args.get('graphToInst', False):
         args['context'] = cuda_code.init_cuda()
     os.makedirs(args['result_folder'], exist_ok=True)
-    affinities = args['affinities']
-    if affinities is not None:
-        if affinities.endswith(".zarr") or os.path.isfile(affinities):
-            do_all(affinities, **args)
-            return
-        elif os.path.isdir(affinities):
-            aff_files = glob.glob(os.path.join(affinities, "*.hdf")) + \
-                glob.glob(os.path.join(affinities, "*.npy"))
-        else:
-            raise RuntimeError("affinities (%s) should be file or dir", affinities)
-    else:
-        aff_files = []
-        if args['mode'] is not None and args['checkpoint'] is not None:
-            aff_files = glob.glob(os.path.join(args['basedir'], args['mode'],
-                                               "processed", args['checkpoint'], "*.hdf"))
-    if args['parallel']:
-        raise NotImplementedError
-    for fl in aff_files:
+    for fl in _input_files(args):
         do_all(fl, **args)
     cuda_code.delete_cuda(args.get('context'))
