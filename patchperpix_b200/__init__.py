@@ -6,7 +6,9 @@ Drop-in for the reference's `PatchPerPix.vote_instances` package on the
     patchperpix_b200.stitch_patch_graph.main(pred_file, **kwargs)
 """
 from . import vote_instances, stitch_patch_graph          # noqa: F401
-from .stitch_patch_graph import get_offsets, get_offset_str  # noqa: F401
+from .stitch_patch_graph import main, get_offsets, get_offset_str  # noqa: F401  (as the reference)
+from .postprocess import clean_mask                         # noqa: F401
 
-__all__ = ['vote_instances', 'stitch_patch_graph', 'cuda_code', 'assembly',
-           'consensus_array', 'ranked_patches', 'aff_patch_graph', 'synth', 'layout']
+__all__ = ['vote_instances', 'stitch_patch_graph', 'cuda_code', 'assembly', 'sharded', 'pipeline',
+           'consensus_array', 'ranked_patches', 'aff_patch_graph', 'postprocess', 'io_util',
+           'decoder', 'synth', 'layout', 'main', 'get_offsets', 'get_offset_str', 'clean_mask']

@@ -16,12 +16,11 @@ Same C-ABI calls, same order, same results as BlockAssembler driven by to_instan
 """
 import collections
 import concurrent.futures
-import ctypes
 
 import numpy as np
 
 from . import cuda_code as cc
-from .assembly import BlockAssembler, RowSource, _latency_stream
+from .assembly import BlockAssembler, RowSource
 
 
 def _torch():

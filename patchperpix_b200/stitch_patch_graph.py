@@ -29,7 +29,7 @@ import numpy as np
 import scipy.spatial
 
 from . import vote_instances as vi
-from .utilVoteInstances import returnFg, numinst_from_prob
+from .utilVoteInstances import numinst_from_prob
 
 logger = logging.getLogger(__name__)
 
