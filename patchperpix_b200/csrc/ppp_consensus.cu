@@ -415,7 +415,8 @@ extern "C" int ppp_consensus_small(const float* rv, const uint16_t* rb16, const 
     cudaError_t e = cudaFuncSetAttribute(consensus_small_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return ppp_fail((int)e, "ppp_consensus_small: smem attribute");
-    consensus_small_kernel<<<(unsigned)F, 128, sm, (cudaStream_t)stream>>>(
+    const int nthr = ((cfg->reserved >> 22) & 3) == 1 ? 64 : ((cfg->reserved >> 22) & 3) == 2 ? 96 : 128;   // (tuning)
+    consensus_small_kernel<<<(unsigned)F, nthr, sm, (cudaStream_t)stream>>>(
         rv, rb16, rbw, flags, fgidx, rowvox, need, F, *cfg, cons, cnt);
     return ppp_check("ppp_consensus_small");
 }
