@@ -375,6 +375,51 @@ def _run_jobs(jobs, fn, workers):
     return out
 
 
+def _neighbour_exchange(mine, send_blocks, nxt, recv_blocks, prv, dev):
+    """pair lists of `send_blocks` to rank `nxt`, those of `recv_blocks` from rank `prv`
+    (None: no such neighbour).  Two messages each way: counts i64 [blocks], pairs i32
+    [sum,6].  Returns {block: (pairs u32 [n,6], None)} for the non-empty received blocks."""
+    import torch
+    dist = _dist()
+    if dist is None or (nxt is None and prv is None):
+        return {}
+    cdev = dev if dist.get_backend() == 'nccl' else torch.device('cpu')
+    ops = []
+    if nxt is not None:
+        cnt = torch.tensor([len(mine[b][1]) if b in mine else 0 for b in send_blocks],
+                           dtype=torch.int64)
+        ops.append(dist.P2POp(dist.isend, cnt.to(cdev), nxt))
+    rc = None
+    if prv is not None:
+        rc = torch.zeros(len(recv_blocks), dtype=torch.int64, device=cdev)
+        ops.append(dist.P2POp(dist.irecv, rc, prv))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    ops = []
+    if nxt is not None and int(cnt.sum()):
+        data = np.concatenate([mine[b][0] for b in send_blocks if b in mine])
+        ops.append(dist.P2POp(dist.isend, torch.from_numpy(
+            np.ascontiguousarray(data).view(np.int32)).to(cdev), nxt))
+    rd = None
+    if prv is not None:
+        rc = rc.cpu().numpy()
+        if int(rc.sum()):
+            rd = torch.empty((int(rc.sum()), 6), dtype=torch.int32, device=cdev)
+            ops.append(dist.P2POp(dist.irecv, rd, prv))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    out = {}
+    if rd is not None:
+        rd = rd.cpu().numpy().view(np.uint32)
+        o = 0
+        for b, n in zip(recv_blocks, rc):
+            if n:
+                out[b] = (rd[o:o + int(n)], None)
+                o += int(n)
+    return out
+
+
 def _allgather_edges(per_job, n_jobs, owner_of):
     """exchange (1)/(2): every rank contributes {job: (pairs, aff)} for the jobs it
     owns; returns the complete {job: (pairs u32 [n,6], aff f32 [n])} on every rank.
@@ -596,12 +641,25 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
         for b, r in zip(my_blocks, res):
             block_done(b, r)
     lap('blocks')
-    # exchange (1) runs on a helper thread: this rank finishes the host part of its
-    # interior faces while the slower ranks finish their blocks
+    # exchange (1), neighbour to neighbour: a face job reads the selected patches of the
+    # lower neighbour block; for the first block row of a slab those belong to the previous
+    # rank, which sends the pair lists of its last block row (send/recv on a helper thread
+    # while this rank finishes the host part of its interior faces).  Nothing global here:
+    # a rank only ever waits for its predecessor.
+    def row_of(b):
+        return (int(offsets[b][axis]) - int(bb_offset[axis])) // int(chunksize[axis])
+    live = [r for r in range(world) if any(o == r for o in owner)]
+    my_rows = sorted({row_of(b) for b in my_blocks})
+    prv = live[live.index(rank) - 1] if rank in live and live.index(rank) > 0 else None
+    nxt = live[live.index(rank) + 1] if rank in live and live.index(rank) + 1 < len(live) else None
+    send_blocks = [b for b in my_blocks if row_of(b) == my_rows[-1]] if nxt is not None else []
+    recv_blocks = [b for b in range(nblk) if owner[b] == prv and my_rows and
+                   row_of(b) == my_rows[0] - 1] if prv is not None else []
+
     def exchange1():
         if shard.dev.type == 'cuda':
             torch.cuda.set_device(shard.dev)
-        box['blocks'] = _allgather_edges(mine, nblk, lambda b: owner[b])
+        box['remote'] = _neighbour_exchange(mine, send_blocks, nxt, recv_blocks, prv, shard.dev)
     ex = threading.Thread(target=exchange1)
     ex.start()
     early_res = {k: f.result() for k, f in early.items()}
@@ -609,25 +667,21 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
         hpool.shutdown()
     lap('faces_host_early')
     ex.join()
-    blocks = box['blocks']
-    lap('allgather_block_edges')
+    box['blocks'] = box['remote']            # where selected_of looks for foreign blocks
+    lap('neighbour_exchange')
 
     # ---- phase 2: face jobs, on the owner of the higher block ------------------------
-    jobs = []
-    first_nonempty = next((b for b in range(nblk) if b in blocks), None)
-    for b in range(nblk):
-        if b not in blocks or b == first_nonempty:
-            continue                                             # :151-156, :178-181
-        for nb, dim in neighbours(b, -1):
-            if nb in blocks:
-                jobs.append((b, nb, dim))
+    # (block, lower neighbour, axis) for both non-empty; the first non-empty block of the
+    # volume has no non-empty lower neighbour, so :151-156 / :178-181 need no special case
+    known = set(mine) | set(box['remote'])
+    my_jobs = [(b, nb, dim) for b in my_blocks if b in mine
+               for nb, dim in neighbours(b, -1) if nb in known]
 
-    def face(j):
-        cp = face_host(jobs[j])
+    def face(job):
+        cp = face_host(job)
         if cp is None:
             return None
         return _face_job(shard, cp[0], cp[1], ps, kwargs, block_fn)
-    my_jobs = [j for j in range(len(jobs)) if owner[jobs[j][0]] == rank]
     if block_fn is not None or not kwargs.get('ppp_batch_faces', True):
         res = _run_jobs(my_jobs, face, workers)
     else:
@@ -635,37 +689,33 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
         # face job reads does not depend on the extent of its region (every centre that can
         # vote on them lies inside: the region is padded by patchshape + patchshape//2,
         # :261-278), so one gate/prepare/consensus/patch-graph pass over the row serves them all
-        late = [j for j in my_jobs if jobs[j] not in early_res]
-        late_res = dict(zip(late, _run_jobs([jobs[j] for j in late], face_host, workers)))
-        host = [early_res[jobs[j]] if jobs[j] in early_res else late_res[j] for j in my_jobs]
+        late = [job for job in my_jobs if job not in early_res]
+        late_res = dict(zip(late, _run_jobs(late, face_host, workers)))
+        host = [early_res[job] if job in early_res else late_res[job] for job in my_jobs]
         lap('faces_host')
         groups = {}
-        for j, cp in zip(my_jobs, host):
+        for job, cp in zip(my_jobs, host):
             if cp is not None:
-                groups.setdefault(int(offsets[jobs[j][0]][axis]), []).append((j, cp))
+                groups.setdefault(int(offsets[job[0]][axis]), []).append((job, cp))
         got = {}
         for part in _run_jobs(sorted(groups), lambda k: _face_batch(shard, groups[k], ps, kwargs),
                               min(workers, 2)):
             got.update(part)
-        res = [got.get(j) for j in my_jobs]
-    my_faces = {j: r for j, r in zip(my_jobs, res) if r is not None}
+        res = [got.get(job) for job in my_jobs]
     lap('faces')
-    faces = _allgather_edges(my_faces, len(jobs), lambda j: owner[jobs[j][0]])  # exchange (2)
-    lap('allgather_face_edges')
-
-    # ---- the global edge list in the reference's order (update_graph calls) -----------
-    plist, alist = [], []
-    jidx = {}
-    for j, (b, nb, dim) in enumerate(jobs):
-        if j in faces:
-            jidx.setdefault(b, []).append(j)
-    for b in sorted(blocks):
-        plist.append(blocks[b][0])
-        alist.append(blocks[b][1])
-        for j in jidx.get(b, ()):
-            plist.append(faces[j][0])
-            alist.append(faces[j][1])
-    info = dict(n_blocks=nblk, n_faces=len(jobs), n_edges=int(sum(len(a) for a in alist)),
+    # exchange (2): ONE all-gather of everything this rank computed, keyed so that sorting
+    # the keys gives the reference's order of update_graph calls: block b, then its faces
+    # towards -z, -y, -x (stitch_patch_graph.py:178-193)
+    contrib = {4 * b: r for b, r in mine.items()}
+    for (b, nb, dim), r in zip(my_jobs, res):
+        if r is not None:
+            contrib[4 * b + 1 + dim] = r
+    edges = _allgather_edges(contrib, 4 * nblk, lambda k: owner[k // 4])
+    lap('allgather_edges')
+    plist = [edges[k][0] for k in sorted(edges)]
+    alist = [edges[k][1] for k in sorted(edges)]
+    n_faces = sum(1 for k in edges if k % 4)
+    info = dict(n_blocks=nblk, n_faces=n_faces, n_edges=int(sum(len(a) for a in alist)),
                 my_blocks=len(my_blocks), my_faces=len(my_jobs), halo_bytes=shard.halo_bytes,
                 phase_ms=tm,
                 rows=int(shard.coords.shape[0]), own_rows=shard.n_own)
