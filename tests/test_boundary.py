@@ -412,3 +412,77 @@ def test_file_level_entry_matches_the_reference_run(tmp_path, rows):
     res = np.load(fn)
     for k in _BB_KEYS:
         assert np.array_equal(res[k], g[k].astype(np.uint16)), k
+
+
+# ---------------------------------------------------------------------------
+# loadAffinities (utilVoteInstances.py:136-251) on real containers
+# ---------------------------------------------------------------------------
+def _store(tmp_path, name, arrays):
+    path = str(tmp_path / name)
+    g = io_util.ZarrLiteGroup(path, 'w')
+    for k, v in arrays.items():
+        g.create_dataset(k, data=v)
+    return path
+
+
+def test_load_affinities_zarr_3d_with_crops_and_numinst(tmp_path):
+    rng = np.random.default_rng(7)
+    pred = rng.random((27, 6, 8, 10)).astype(np.float16)
+    prob = rng.random((3, 6, 8, 10)).astype(np.float32)
+    path = _store(tmp_path, 's.zarr', {'volumes/pred_affs': pred, 'volumes/pred_numinst': prob})
+    kw = dict(aff_key='volumes/pred_affs', numinst_key='volumes/pred_numinst', fg_key=None,
+              patch_threshold=0.5, numinst_threshs=[0.9, 0.1])
+    aff, numinst, fg = uvi.loadAffinities(path, '', patchshape=np.array([3, 3, 3]), **kw)
+    assert aff.shape == (27, 6, 8, 10) and np.array_equal(aff, pred)
+    want = np.zeros((6, 8, 10), np.uint8)
+    want[prob[1] > 0.9] = 1
+    want[prob[2] > 0.1] = 2
+    assert np.array_equal(np.squeeze(numinst), want)
+    assert np.array_equal(np.squeeze(fg), want > 0)
+    # crop_*_s / crop_*_e (:171-200)
+    aff_c, _, _ = uvi.loadAffinities(path, '', patchshape=np.array([3, 3, 3]),
+                                     **dict(kw, crop_z_s=1, crop_z_e=5, crop_y_s=2, crop_x_e=7))
+    assert np.array_equal(aff_c, pred[:, 1:5, 2:, :7])
+
+
+def test_load_affinities_channel_last_2d_and_logits(tmp_path):
+    """2-D predictions are lifted to Z = 1, a channel-last array is rotated (:158-164),
+    stored logits are squashed with expit (:249-250)."""
+    rng = np.random.default_rng(8)
+    logits = (rng.normal(0, 3, (12, 14, 25))).astype(np.float16)      # [Y,X,P], P = 5x5
+    fgp = rng.random((1, 12, 14)).astype(np.float32)
+    path = _store(tmp_path, 'l.zarr', {'volumes/pred_affs': logits, 'volumes/pred_fgbg': fgp})
+    aff, numinst, fg = uvi.loadAffinities(path, '', patchshape=np.array([1, 5, 5]),
+                                          aff_key='volumes/pred_affs', numinst_key=None,
+                                          fg_key='volumes/pred_fgbg', patch_threshold=0.5)
+    assert aff.shape == (25, 1, 12, 14)
+    want = 1.0 / (1.0 + np.exp(-np.moveaxis(logits, -1, 0).astype(np.float32)))
+    assert np.allclose(aff[:, 0], want, atol=1e-6)
+    assert numinst is None
+    # the foreground comes from the container as stored (loadFg, :275-303), here fg_key
+    assert np.array_equal(np.squeeze(fg), fgp[0] > 0.5)
+
+
+def test_load_affinities_skips_finished_samples(tmp_path):
+    """utilVoteInstances.py:146-149: a container that already holds the result is skipped."""
+    pred = np.zeros((9, 1, 4, 4), np.float16)
+    path = _store(tmp_path, 'd.zarr', {'volumes/pred_affs': pred,
+                                       'vote_instances_05_tfgc': np.zeros((1, 4, 4), np.uint16)})
+    assert uvi.loadAffinities(path, '_05_tfgc', patchshape=np.array([1, 3, 3]),
+                              aff_key='volumes/pred_affs', patch_threshold=0.5) is None
+
+
+def test_slab_partition_is_optimal_on_small_cases():
+    """the dynamic programme against brute force over all contiguous splits."""
+    import itertools
+    from patchperpix_b200 import sharded
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        n, world = int(rng.integers(3, 9)), int(rng.integers(2, 5))
+        w = rng.integers(1, 20, n)
+        _, slabs = sharded.slab_partition((8, n * 10, 8), (8, 10, 8), world, axis=1, weights=w)
+        got = max(int(w[lo // 10:hi // 10].sum()) for lo, hi in slabs)
+        best = min(max(int(w[a:b].sum()) for a, b in zip((0,) + cuts, cuts + (n,)))
+                   for cuts in itertools.combinations_with_replacement(range(n + 1), world - 1))
+        assert got == best, (w, slabs)
+        assert slabs[0][0] == 0 and max(hi for lo, hi in slabs) == n * 10
