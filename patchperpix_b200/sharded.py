@@ -15,11 +15,14 @@ lives and who does what:
   * exchange (0), NCCL send/recv: the rows within `2*ps + ps//2` of a slab
     border go to the neighbouring rank (block input halo + the face regions that
     reach across the border) -- fg-compacted rows, not dense planes;
-  * every rank assembles the blocks of its slab (to_instance_seg on a RowSource);
-  * exchange (1), tensor all-gather of the per-block edge lists (pairs u32 [n,6],
-    aff f32 [n], padded to the largest rank);
-  * face job (block, lower neighbour) runs on the owner of `block`;
-  * exchange (2), tensor all-gather of the face edges;
+  * every rank assembles the blocks of its slab: one host thread keeps many blocks in
+    flight on several CUDA streams (pipeline.py);
+  * exchange (1), neighbour send/recv: the pair lists of a rank's last block row go to
+    the next rank, whose first block row has its lower face neighbours there;
+  * face job (block, lower neighbour) runs on the owner of `block`; all face jobs of a
+    block row are served by ONE consensus / patch-graph pass over the row's region;
+  * exchange (2), ONE tensor all-gather of all block and face edge lists (pairs u32
+    [n,6], aff f32 [n], padded to the largest rank);
   * every rank builds the global edge list in the reference's order and runs the
     same deterministic partition (ppp_label_cc on compacted node ids, or the
     mutex watershed), then paints the nodes whose windows touch ITS slab from the
@@ -31,6 +34,7 @@ a digest) and equal to the dense single-process driver (stitch_arrays).
 import concurrent.futures
 import logging
 import threading
+import time
 
 import numpy as np
 
@@ -542,7 +546,6 @@ def stitch_shard(shard, slabs, workers=None, block_fn=None, paint_fn=None, **kwa
         raise ValueError("coordinate %d outside every slab" % coord)
     owner = [slab_of(int(o[axis])) for o in offsets]
 
-    import time
     tm = {}
     t_last = [time.perf_counter()]
 
