@@ -6,9 +6,13 @@ decode.py:102-109) or hdf, caches per-block results in a zarr next to the output
 (vote_instances.py:542-554, stitch_patch_graph.py:849-894).  zarr and h5py are
 optional packages; when zarr is missing, `ZarrLite` below reads and writes the
 zarr v2 directory layout itself (C order, chunked, compressor null / zlib / gzip /
-zstd) -- enough for the bundled flylight sample (gzip chunks), for stores written
-by this package and for uncompressed or zlib/gzip/zstd stores of a predict run.
-Blosc-framed chunks need the real zarr + numcodecs packages: the error says so.
+zstd / blosc) -- enough for the bundled flylight sample (gzip chunks), for stores
+written by this package and for the stores of a predict run.
+Blosc frames (what predict_no_gp.py:243-257 writes: zstd, bit-shuffle) are unpacked by
+`blosc_decode` below, written from the c-blosc 1.x chunk format; no Blosc encoder
+exists in this image, so it is checked against frames built by the tests' own
+encoder (tests/test_boundary.py), not against numcodecs output -- with zarr +
+numcodecs installed `open_container` uses those and never reaches it.
 `.npz` is the always-available result format.
 """
 import itertools
@@ -35,8 +39,102 @@ def _decompress(buf, comp, path):
         return zlib.decompress(buf, 16 + zlib.MAX_WBITS)
     if cid == 'zstd':
         return _zstd_decompress(buf)
+    if cid == 'blosc':
+        return blosc_decode(buf, path)
     raise RuntimeError("%s: chunks are compressed with %r; install zarr + numcodecs to read "
-                       "this store (ZarrLite handles null, zlib, gzip, zstd)" % (path, cid))
+                       "this store (ZarrLite handles null, zlib, gzip, zstd, blosc)" % (path, cid))
+
+
+_BLOSC_MAX_SPLITS, _BLOSC_MIN_BUFFERSIZE = 16, 128
+
+
+def _blosc_codec(code, path):
+    """compressor format in bits 5-7 of the flags byte -> f(bytes, size) -> bytes."""
+    import pyarrow as pa
+    if code == 4:
+        return lambda b, n: pa.Codec('zstd').decompress(b, decompressed_size=n, asbytes=True)
+    if code == 3:
+        return lambda b, n: zlib.decompress(b)
+    if code == 1:
+        return lambda b, n: pa.Codec('lz4_raw').decompress(b, decompressed_size=n, asbytes=True)
+    if code == 2:
+        return lambda b, n: pa.Codec('snappy').decompress(b, decompressed_size=n, asbytes=True)
+    raise RuntimeError("%s: blosc frame with internal codec %d (blosclz) is not supported; "
+                       "install zarr + numcodecs" % (path, code))
+
+
+def _bit_unshuffle(block, typesize):
+    """inverse of bitshuffle's bit transpose over whole elements: the input holds, for
+    byte j of the element and bit k of that byte, one row of size/8 bytes whose bit i%8
+    of byte i/8 (least significant first) belongs to element i.  c-blosc 1.x shuffles
+    only blocks whose element count is a multiple of 8 and copies any other block."""
+    n = len(block)
+    size = n // typesize
+    if size % 8 != 0 or size == 0:
+        return block
+    body = np.frombuffer(block, np.uint8, size * typesize).reshape(typesize, 8, size // 8)
+    bits = np.unpackbits(body, axis=-1, bitorder='little')              # [j][k][i]
+    out = np.packbits(bits.transpose(2, 0, 1), axis=-1, bitorder='little')  # [i][j][1]
+    return out.tobytes() + bytes(block[size * typesize:])
+
+
+def _byte_unshuffle(block, typesize):
+    n = len(block)
+    q = n // typesize
+    body = np.frombuffer(block, np.uint8, q * typesize).reshape(typesize, q)
+    return np.ascontiguousarray(body.T).tobytes() + bytes(block[q * typesize:])
+
+
+def blosc_decode(buf, path='<buffer>'):
+    """one c-blosc 1.x chunk -> bytes.  16-byte header: version, versionlz, flags,
+    typesize, nbytes, blocksize, cbytes (u32 little endian); flags: 0x1 byte shuffle,
+    0x2 stored uncompressed, 0x4 bit shuffle, 0x10 blocks not split, bits 5-7 the codec.
+    Then one i32 start offset per block; a block is `typesize` streams (one per byte of the
+    element, when split) or one stream, each an i32 length + data, stored raw when the
+    length equals the stream's uncompressed size."""
+    buf = bytes(buf)
+    if len(buf) < 16:
+        raise RuntimeError("%s: truncated blosc chunk" % path)
+    flags, typesize = buf[2], buf[3]
+    nbytes, blocksize, cbytes = (int.from_bytes(buf[o:o + 4], 'little') for o in (4, 8, 12))
+    if cbytes != len(buf):
+        raise RuntimeError("%s: blosc header says %d bytes, the chunk has %d" % (path, cbytes, len(buf)))
+    if nbytes == 0:
+        return b''
+    if flags & 0x2:
+        return buf[16:16 + nbytes]
+    codec = _blosc_codec(flags >> 5, path)
+    shuffle = bool(flags & 0x1) and typesize > 1
+    bitshuffle = bool(flags & 0x4)
+    nblocks = (nbytes + blocksize - 1) // blocksize
+    out = []
+    for b in range(nblocks):
+        bsize = min(blocksize, nbytes - b * blocksize)
+        leftover = bsize != blocksize
+        split = (not (flags & 0x10) and typesize <= _BLOSC_MAX_SPLITS and
+                 blocksize // typesize >= _BLOSC_MIN_BUFFERSIZE and not leftover)
+        nsplits = typesize if split else 1
+        ne = bsize // nsplits
+        pos = int.from_bytes(buf[16 + 4 * b:20 + 4 * b], 'little', signed=True)
+        parts = []
+        for _ in range(nsplits):
+            cb = int.from_bytes(buf[pos:pos + 4], 'little', signed=True)
+            pos += 4
+            if cb < 0 or pos + cb > len(buf):
+                raise RuntimeError("%s: corrupt blosc block %d" % (path, b))
+            part = buf[pos:pos + cb] if cb == ne else codec(buf[pos:pos + cb], ne)
+            if len(part) != ne:
+                raise RuntimeError("%s: blosc block %d unpacked to %d bytes, expected %d"
+                                   % (path, b, len(part), ne))
+            parts.append(part)
+            pos += cb
+        block = b''.join(parts)
+        if shuffle:
+            block = _byte_unshuffle(block, typesize)
+        elif bitshuffle and bsize >= typesize:
+            block = _bit_unshuffle(block, typesize)
+        out.append(block)
+    return b''.join(out)
 
 
 def _zstd_decompress(buf):

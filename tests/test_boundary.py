@@ -7,6 +7,7 @@ functions (file:line in each test); the GPU tests run the entry points."""
 import json
 import os
 import zipfile
+import zlib
 
 import numpy as np
 import pytest
@@ -56,14 +57,124 @@ def test_zarrlite_roundtrip(tmp_path):
         assert np.array_equal(z[171 % 5:4, -1], a[1:4, -1])
         assert np.array_equal(z[..., 3:5], a[..., 3:5])
     assert 'volumes/gz' in r and 'volumes' in r and 'volumes/nope' not in r
-    with pytest.raises(RuntimeError, match='blosc'):
-        io_util._decompress(b'', {'id': 'blosc'}, 'chunk')
+    with pytest.raises(RuntimeError, match='lzma'):
+        io_util._decompress(b'', {'id': 'lzma'}, 'chunk')
 
 
 def test_zstd_chunks_through_pyarrow():
     pa = pytest.importorskip('pyarrow')
     raw = np.arange(5000, dtype=np.uint16).tobytes()
     assert io_util._zstd_decompress(pa.Codec('zstd').compress(raw, asbytes=True)) == raw
+
+
+def _bitshuffle_by_stages(block, ts):
+    """bitshuffle's scalar route, stage by stage (byte transpose of the elements, 8x8 bit
+    transposes of consecutive bytes into eight bit rows, regrouping of the bit rows per
+    element byte), written with plain loops: the forward direction, independent of the
+    closed form io_util._bit_unshuffle inverts."""
+    size = len(block) // ts
+    if size % 8 or size == 0:
+        return bytes(block)                      # c-blosc 1.x copies such a block
+    n = size * ts
+    a = bytearray(n)
+    for i in range(size):                        # stage 1: [i][j] -> [j][i]
+        for j in range(ts):
+            a[j * size + i] = block[i * ts + j]
+    rowlen = n // 8
+    b = bytearray(n)
+    for ii in range(rowlen):                     # stage 2: bit k of bytes 8ii..8ii+7 -> row k
+        for k in range(8):
+            v = 0
+            for q in range(8):
+                v |= ((a[8 * ii + q] >> k) & 1) << q
+            b[k * rowlen + ii] = v
+    c = bytearray(n)
+    per = size // 8
+    for k in range(8):                           # stage 3: [k][j][per] -> [j][k][per]
+        for j in range(ts):
+            c[(j * 8 + k) * per:(j * 8 + k + 1) * per] = b[(k * ts + j) * per:(k * ts + j + 1) * per]
+    return bytes(c) + bytes(block[n:])
+
+
+def _blosc_frame(raw, ts, blocksize, mode, codec, split=True):
+    """a c-blosc 1.x chunk built from the format description (header, block starts, per-block
+    streams with i32 lengths, raw storage when compression does not shrink a stream)."""
+    import pyarrow as pa
+    comp = {4: lambda x: pa.Codec('zstd').compress(x, asbytes=True),
+            3: lambda x: zlib.compress(x, 1),
+            1: lambda x: pa.Codec('lz4_raw').compress(x, asbytes=True)}[codec]
+    nblocks = (len(raw) + blocksize - 1) // blocksize
+    flags = (codec << 5) | {0: 0, 1: 0x1, 2: 0x4}[mode] | (0 if split else 0x10)
+    body, starts = b'', []
+    for b in range(nblocks):
+        blk = raw[b * blocksize:(b + 1) * blocksize]
+        if mode == 1 and ts > 1:
+            q = len(blk) // ts
+            blk = b''.join(bytes(blk[j:q * ts:ts]) for j in range(ts)) + blk[q * ts:]
+        elif mode == 2 and len(blk) >= ts:
+            blk = _bitshuffle_by_stages(blk, ts)
+        do_split = split and ts <= 16 and blocksize // ts >= 128 and len(blk) == blocksize
+        ns = ts if do_split else 1
+        ne = len(blk) // ns
+        starts.append(16 + 4 * nblocks + len(body))
+        for j in range(ns):
+            part = blk[j * ne:(j + 1) * ne]
+            c = comp(part)
+            if len(c) >= ne:
+                c = part
+            body += len(c).to_bytes(4, 'little') + c
+    head = bytes([2, 1, flags, ts]) + len(raw).to_bytes(4, 'little') + blocksize.to_bytes(4, 'little')
+    total = 16 + 4 * nblocks + len(body)
+    return head + total.to_bytes(4, 'little') + b''.join(x.to_bytes(4, 'little') for x in starts) + body
+
+
+def test_blosc_chunks(tmp_path):
+    """Blosc frames as predict_no_gp.py:243-257 writes them (zstd, bit-shuffle) and the other
+    shapes a frame can take: byte shuffle, no shuffle, split and unsplit blocks, a short
+    last block, streams stored raw, the whole chunk stored raw.  The encoder above is the
+    test's own (no Blosc library exists in this image)."""
+    pytest.importorskip('pyarrow')
+    rng = np.random.default_rng(5)
+    smooth = (np.cumsum(rng.integers(0, 3, 6000)) % 2048).astype(np.float16)
+    noise = rng.integers(0, 65536, 3000).astype(np.uint16)
+    for arr in (smooth, noise, smooth.astype(np.float32), smooth[:1003].astype(np.uint8)):
+        raw, ts = arr.tobytes(), arr.dtype.itemsize
+        for blocksize in (512, 2048, 4096 + 8 * ts, len(raw), 2 * len(raw)):
+            for mode in (0, 1, 2):
+                for codec, split in ((4, True), (4, False), (3, True), (1, False)):
+                    fr = _blosc_frame(raw, ts, blocksize, mode, codec, split)
+                    assert io_util.blosc_decode(fr) == raw, (arr.dtype, blocksize, mode, codec, split)
+    # stored uncompressed (flag 0x2): the data follows the header
+    fr = bytes([2, 1, 0x2 | 0x4 | (4 << 5), 2]) + (10).to_bytes(4, 'little') + \
+        (10).to_bytes(4, 'little') + (26).to_bytes(4, 'little') + bytes(range(10))
+    assert io_util.blosc_decode(fr) == bytes(range(10))
+    with pytest.raises(RuntimeError, match='header says'):
+        io_util.blosc_decode(fr + b'x')
+    with pytest.raises(RuntimeError, match='blosclz'):
+        io_util.blosc_decode(_blosc_frame(b'ab' * 600, 2, 2400, 0, 4)[:2] + bytes([0]) +
+                             _blosc_frame(b'ab' * 600, 2, 2400, 0, 4)[3:])
+    # a store whose .zarray names the blosc compressor, read through ZarrLite
+    a = (rng.random((3, 6, 10, 8)) * 0.9).astype(np.float16)
+    d = tmp_path / 'b.zarr' / 'volumes' / 'pred_affs'
+    os.makedirs(d)
+    chunks = (3, 4, 10, 8)
+    with open(d / '.zarray', 'w') as f:
+        json.dump(dict(zarr_format=2, shape=a.shape, chunks=chunks, dtype='<f2', order='C',
+                       fill_value=0, filters=None,
+                       compressor=dict(id='blosc', cname='zstd', clevel=3, shuffle=2, blocksize=0)), f)
+    with open(tmp_path / 'b.zarr' / '.zgroup', 'w') as f:
+        json.dump(dict(zarr_format=2), f)
+    with open(tmp_path / 'b.zarr' / 'volumes' / '.zgroup', 'w') as f:
+        json.dump(dict(zarr_format=2), f)
+    for c in range(2):
+        blk = np.zeros(chunks, np.float16)
+        part = a[:, 4 * c:4 * c + 4]
+        blk[:, :part.shape[1]] = part
+        with open(d / ('0.%d.0.0' % c), 'wb') as f:
+            f.write(_blosc_frame(blk.tobytes(), 2, 1024, 2, 4))
+    z = io_util.ZarrLiteGroup(str(tmp_path / 'b.zarr'))['volumes/pred_affs']
+    assert np.array_equal(np.array(z), a)
+    assert np.array_equal(z[:, 3:6, 2:5], a[:, 3:6, 2:5])
 
 
 @pytest.mark.skipif(not os.path.exists(REF_ZIP), reason="reference tree absent")
