@@ -35,7 +35,14 @@
 
 namespace {
 
-struct MwsEdge { int u, v; float w; bool attractive; };
+struct MwsEdge { int u, v; float aff; };             // aff signed: > 0 attractive
+
+inline uint32_t abs_bits(float a)
+{
+    uint32_t k;
+    memcpy(&k, &a, 4);
+    return k & 0x7fffffffu;
+}
 
 // open addressing, u64 key -> int value, sized once (keys are never removed)
 struct FlatMap {
@@ -64,26 +71,77 @@ struct FlatMap {
     }
 };
 
+// growing set of u64 keys (open addressing, half full at most)
+struct FlatSet {
+    std::vector<uint64_t> key;
+    size_t mask, used;
+    FlatSet() : key(1024, ~0ULL), mask(1023), used(0) {}
+    static size_t home(uint64_t k, size_t mask)
+    {
+        return (size_t)((k * 0x9E3779B97F4A7C15ULL) >> 20) & mask;
+    }
+    bool contains(uint64_t k) const
+    {
+        for (size_t i = home(k, mask);; i = (i + 1) & mask) {
+            if (key[i] == k) return true;
+            if (key[i] == ~0ULL) return false;
+        }
+    }
+    bool insert(uint64_t k)                              // false: was there already
+    {
+        for (size_t i = home(k, mask);; i = (i + 1) & mask) {
+            if (key[i] == k) return false;
+            if (key[i] == ~0ULL) { key[i] = k; break; }
+        }
+        if (++used * 2 > mask) {
+            std::vector<uint64_t> old;
+            old.swap(key);
+            mask = mask * 2 + 1;
+            key.assign(mask + 1, ~0ULL);
+            for (uint64_t q : old)
+                if (q != ~0ULL) {
+                    size_t i = home(q, mask);
+                    while (key[i] != ~0ULL) i = (i + 1) & mask;
+                    key[i] = q;
+                }
+        }
+        return true;
+    }
+};
+
+// clusters with their mutual exclusions.  The relation "root a must not join root b" is
+// one set of root pairs; every root also keeps the list of partners it was ever excluded
+// from (ids that may have been merged away since: find() gives their present root), so
+// that a join can re-key the pairs of the root that disappears.  Pairs of a vanished root
+// stay in the set: a non-root is never asked about again.
 struct Clusters {
     std::vector<int> parent;
-    std::vector<std::unordered_set<int>> mutex;      // by root: roots it must not join
-    explicit Clusters(int n) : parent(n), mutex(n) { for (int i = 0; i < n; i++) parent[i] = i; }
+    std::vector<std::vector<int>> partners;
+    FlatSet pairs;
+    explicit Clusters(int n) : parent(n), partners(n) { for (int i = 0; i < n; i++) parent[i] = i; }
+    static uint64_t pair_key(int a, int b)
+    {
+        return ((uint64_t)(uint32_t)std::min(a, b) << 32) | (uint32_t)std::max(a, b);
+    }
     int find(int a) {
         while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; }
         return a;
     }
-    bool exclusive(int a, int b) const { return mutex[a].count(b) != 0; }
-    void forbid(int a, int b) { if (a != b) { mutex[a].insert(b); mutex[b].insert(a); } }
+    bool exclusive(int a, int b) const { return pairs.used != 0 && pairs.contains(pair_key(a, b)); }
+    void forbid(int a, int b) {
+        if (a == b || !pairs.insert(pair_key(a, b))) return;
+        partners[a].push_back(b);
+        partners[b].push_back(a);
+    }
     int join(int a, int b) {                          // returns the surviving root
         if (a == b) return a;
-        if (mutex[a].size() < mutex[b].size()) std::swap(a, b);
+        if (partners[a].size() < partners[b].size()) std::swap(a, b);
         parent[b] = a;
-        for (int c : mutex[b]) {
-            mutex[c].erase(b);
-            mutex[c].insert(a);
-            mutex[a].insert(c);
+        for (int x : partners[b]) {
+            const int c = find(x);
+            if (c != a && pairs.insert(pair_key(a, c))) partners[a].push_back(c);
         }
-        std::unordered_set<int>().swap(mutex[b]);
+        std::vector<int>().swap(partners[b]);
         return a;
     }
 };
@@ -118,10 +176,6 @@ extern "C" int ppp_mws_host(const uint32_t* pairs, const float* aff, int64_t n,
     FlatMap id_hash(direct ? 0 : 2 * n);
     if (direct) id_direct.assign((size_t)V, -1);
     std::vector<int64_t> vox;
-    std::vector<int> eu, ev;                             // distinct edges in insertion order
-    std::vector<float> weight;
-    FlatMap slot_of(n);                                  // unordered node pair -> slot
-    eu.reserve(n); ev.reserve(n); weight.reserve(n);
     auto node = [&](const uint32_t* c) {
         const int64_t v = ((int64_t)c[0] * Y + c[1]) * X + c[2];
         if (direct && v < V) {
@@ -134,61 +188,73 @@ extern "C" int ppp_mws_host(const uint32_t* pairs, const float* aff, int64_t n,
         if (fresh) vox.push_back(v);
         return id;
     };
+    // the rows with a non-zero affinity, as (earlier node, later node, aff)
+    std::vector<int> rlo, rhi;
+    std::vector<float> raff;
+    rlo.reserve(n); rhi.reserve(n); raff.reserve(n);
     for (int64_t i = 0; i < n; i++) {
         if (aff[i] == 0.0f) continue;                     // aff_patch_graph.py:36
         const int u = node(pairs + 6 * i), v = node(pairs + 6 * i + 3);
-        const uint64_t key = ((uint64_t)(uint32_t)std::min(u, v) << 32) | (uint32_t)std::max(u, v);
-        bool fresh;
-        int& s = slot_of.at(key, (int)weight.size(), &fresh);
-        if (!fresh) { weight[s] = aff[i]; continue; }     // attribute overwritten
-        weight.push_back(aff[i]);
-        eu.push_back(u);
-        ev.push_back(v);
+        rlo.push_back(std::min(u, v));
+        rhi.push_back(std::max(u, v));
+        raff.push_back(aff[i]);
     }
     lapse("graph");
     const int nn = (int)vox.size();
-    const int ne = (int)weight.size();
-    // adjacency in insertion order (CSR): networkx yields, for every node in insertion
-    // order, its neighbours in insertion order, each edge once
-    std::vector<int> deg(nn + 1, 0);
-    for (int e = 0; e < ne; e++) { deg[eu[e] + 1]++; if (ev[e] != eu[e]) deg[ev[e] + 1]++; }
-    for (int i = 0; i < nn; i++) deg[i + 1] += deg[i];
-    std::vector<int> fill(deg.begin(), deg.end() - 1), anb(deg[nn]), aslot(deg[nn]);
-    for (int e = 0; e < ne; e++) {
-        anb[fill[eu[e]]] = ev[e]; aslot[fill[eu[e]]++] = e;
-        if (ev[e] != eu[e]) { anb[fill[ev[e]]] = eu[e]; aslot[fill[ev[e]]++] = e; }
+    const int64_t nr = (int64_t)raff.size();
+    // networkx yields, for every node in insertion order, its neighbours in insertion order,
+    // each edge once: from the EARLIER of its two nodes, at the place the pair was first
+    // added to that node's neighbour list -- the order of the rows whose earlier node it is.
+    // Stable counting sort by the earlier node; a pair that comes again keeps its place and
+    // takes the later affinity (the attribute is overwritten).
+    std::vector<int64_t> start((size_t)nn + 1, 0);
+    for (int64_t i = 0; i < nr; i++) start[rlo[i] + 1]++;
+    for (int i = 0; i < nn; i++) start[i + 1] += start[i];
+    std::vector<int> s_hi((size_t)nr);
+    std::vector<float> s_aff((size_t)nr);
+    {
+        std::vector<int64_t> fill(start.begin(), start.end() - 1);
+        for (int64_t i = 0; i < nr; i++) {
+            const int64_t q = fill[rlo[i]]++;
+            s_hi[q] = rhi[i];
+            s_aff[q] = raff[i];
+        }
     }
     std::vector<MwsEdge> edges;
-    edges.reserve(ne);
-    for (int u = 0; u < nn; u++)
-        for (int q = deg[u]; q < deg[u + 1]; q++) {
-            if (anb[q] < u) continue;                     // seen from the earlier node
-            const float a = weight[aslot[q]];
-            edges.push_back({u, anb[q], a > 0 ? a : -a, a > 0});        // graph_mws.py:22-26
-        }
+    edges.reserve((size_t)nr);
+    {
+        std::vector<int> stamp((size_t)nn, -1), where((size_t)nn, 0);
+        for (int u = 0; u < nn; u++)
+            for (int64_t q = start[u]; q < start[u + 1]; q++) {
+                const int v = s_hi[q];
+                if (stamp[v] != u) {
+                    stamp[v] = u;
+                    where[v] = (int)edges.size();
+                    edges.push_back({u, v, s_aff[q]});    // graph_mws.py:22-26
+                } else {
+                    edges[where[v]].aff = s_aff[q];
+                }
+            }
+    }
     lapse("edges");
-    // stable sort by |aff|, descending (:28): LSD radix sort on the float bits
-    // (non-negative floats order like their bit patterns; the key is complemented)
+    // stable sort by |aff|, descending (:28): LSD radix sort on the float bits of |aff|
+    // (non-negative floats order like their bit patterns; the key is complemented),
+    // 11 + 10 + 10 bits
     {
         std::vector<MwsEdge> tmp(edges.size());
         std::vector<MwsEdge>* src = &edges;
         std::vector<MwsEdge>* dst = &tmp;
-        for (int pass = 0; pass < 4; pass++) {
-            size_t hist[257] = {0};
-            for (const MwsEdge& e : *src) {
-                uint32_t k;
-                memcpy(&k, &e.w, 4);
-                hist[((~k) >> (8 * pass) & 255u) + 1]++;
-            }
-            for (int i = 0; i < 256; i++) hist[i + 1] += hist[i];
-            for (const MwsEdge& e : *src) {
-                uint32_t k;
-                memcpy(&k, &e.w, 4);
-                (*dst)[hist[(~k) >> (8 * pass) & 255u]++] = e;
-            }
+        const int shift[3] = {0, 11, 21}, bits[3] = {11, 10, 10};
+        for (int pass = 0; pass < 3; pass++) {
+            const uint32_t dm = (1u << bits[pass]) - 1u;
+            std::vector<size_t> hist((size_t)dm + 2, 0);
+            for (const MwsEdge& e : *src) hist[(((~abs_bits(e.aff)) >> shift[pass]) & dm) + 1]++;
+            for (uint32_t i = 0; i <= dm; i++) hist[i + 1] += hist[i];
+            for (const MwsEdge& e : *src)
+                (*dst)[hist[((~abs_bits(e.aff)) >> shift[pass]) & dm]++] = e;
             std::swap(src, dst);
         }
-        // four passes: the result is back in `edges`
+        edges.swap(tmp);                                  // three passes: the result is in tmp
     }
     lapse("sort");
 
@@ -199,7 +265,7 @@ extern "C" int ppp_mws_host(const uint32_t* pairs, const float* aff, int64_t n,
     int max_id = 0;                       // np.max(node_CCs.values())
     for (const MwsEdge& e : edges) {
         int a = cl.find(e.u), b = cl.find(e.v);
-        if (!e.attractive) { cl.forbid(a, b); continue; }
+        if (!(e.aff > 0)) { cl.forbid(a, b); continue; }
         int ca = cid[a], cb = cid[b];
         if (ca == 0 && cb == 0) {                         // :37-43 (no mutex test here)
             int id = max_id + 1;

@@ -52,6 +52,47 @@ def test_cabi_mws_random_graphs(gi):
     assert top >= (labels.max() if len(labels) else 0)   # ids ever created
 
 
+@pytest.mark.parametrize('seed,rep,big_space', [(1, 0.1, False), (2, 0.5, True), (3, 0.9, False)])
+def test_cabi_mws_stress_against_oracle(seed, rep, big_space):
+    """larger seeded graphs than the recorded ones -- repeated pairs in both orientations
+    (the later affinity wins, the place in the neighbour list stays), self pairs, tied
+    |aff|, many exclusions, sparse and compact voxel spaces -- against the oracle
+    restatement (itself pinned on the reference's graphs above)."""
+    import networkx as nx
+    from oracle import host_logic
+    rng = np.random.default_rng(seed)
+    Z, Y, X = (40, 300, 300) if big_space else (2, 30, 30)
+    m, n = 700, 6000
+    pts = np.unique(np.stack([rng.integers(0, Z, m), rng.integers(0, Y, m),
+                              rng.integers(0, X, m)], 1), axis=0)
+    pts = pts[rng.permutation(len(pts))]
+    i, j = rng.integers(0, len(pts), n), rng.integers(0, len(pts), n)
+    j[:200] = i[:200]                                           # self pairs
+    i[200:700], j[200:700] = j[5200:5700], i[5200:5700]         # repeats, other orientation
+    i[700:900], j[700:900] = i[5700:5900], j[5700:5900]         # repeats, same orientation
+    aff = np.round(rng.random(n) * 0.95 + 0.02, 2).astype(np.float32)   # many ties
+    aff[rng.random(n) < rep] *= -1
+    aff[:200] = np.abs(aff[:200])
+    aff[rng.random(n) < 0.02] = 0
+    pairs = np.concatenate([pts[i], pts[j]], 1).astype(np.uint32)
+    g = nx.Graph()
+    for k, a in enumerate(aff):
+        if a != 0:
+            g.add_edge(tuple(int(v) for v in pairs[k, :3]), tuple(int(v) for v in pairs[k, 3:]),
+                       aff=a)
+    lab = {}
+    for k, comp in enumerate(host_logic.mutex_watershed(g)):
+        for nd in comp:
+            lab[nd] = k + 1
+    nodes = np.array(list(g.nodes()), np.int64)
+    want = np.array([lab.get(tuple(int(v) for v in nd), 0) for nd in nodes], np.int32)
+    cfg = cc.make_cfg((Z, Y, X), (1, 3, 3), patch_threshold=0.5, fc_threshold=0.5)
+    vox, got, top = mutex_watershed(pairs, aff, cfg)
+    assert np.array_equal(vox, (nodes[:, 0] * Y + nodes[:, 1]) * X + nodes[:, 2])
+    assert np.array_equal(got, want)
+    assert len(np.unique(got)) > 3
+
+
 def test_cabi_mws_empty():
     cfg = cc.make_cfg((1, 8, 8), (1, 3, 3), patch_threshold=0.5, fc_threshold=0.5)
     vox, lab, top = mutex_watershed(np.zeros((0, 6), np.uint32), np.zeros(0, np.float32), cfg)
