@@ -73,8 +73,14 @@ def _bit_unshuffle(block, typesize):
     if size % 8 != 0 or size == 0:
         return block
     body = np.frombuffer(block, np.uint8, size * typesize).reshape(typesize, 8, size // 8)
-    bits = np.unpackbits(body, axis=-1, bitorder='little')              # [j][k][i]
-    out = np.packbits(bits.transpose(2, 0, 1), axis=-1, bitorder='little')  # [i][j][1]
+    # one 64-bit word per (element byte j, group of 8 elements): byte k of the word is the
+    # group's byte of bit row k; transposing the word's 8x8 bit matrix turns it into the
+    # eight element bytes (three masked swaps)
+    x = np.ascontiguousarray(body.transpose(0, 2, 1)).view('<u8')[..., 0]
+    for sh, msk in ((7, 0x00AA00AA00AA00AA), (14, 0x0000CCCC0000CCCC), (28, 0x00000000F0F0F0F0)):
+        t = (x ^ (x >> np.uint64(sh))) & np.uint64(msk)
+        x = x ^ t ^ (t << np.uint64(sh))
+    out = np.ascontiguousarray(x.view(np.uint8).reshape(typesize, size).T)   # [i][j]
     return out.tobytes() + bytes(block[size * typesize:])
 
 
